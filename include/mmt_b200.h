@@ -1,0 +1,213 @@
+/* mmt_b200 -- C ABI of the B200-native (sm_100a) MMT hot path.
+ *
+ * The reference (gabeur/mmt) is pure Python/PyTorch and has NO native interface; the seam a
+ * maintainer binds is the Python plugin surface `model.model.{CENet, sharded_cross_view_inner_product}`
+ * and `model.loss.MaxMarginRankingLoss` (reference train.py:86-93, trainer/trainer.py:27,178-204;
+ * SURVEY.md §8(b)).  Each entry point below replaces the ATen op sequence of the cited reference
+ * lines; the ctypes binding that calls them lives in mmt_b200/_lib.py and INTEGRATION.md shows
+ * the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only: every pointer is a DEVICE pointer to fp32 (or int32 where
+ *     noted) owned by the caller (PyTorch owns all memory); `stream` is a cudaStream_t passed as
+ *     void*.  All launches are asynchronous on that stream; nothing synchronises.
+ *   - return 0 on success, a negative MMT_E* code for argument/shape errors (checked before any
+ *     launch), a positive value = cudaError_t.  mmt_last_error() returns the message.
+ *   - row-major everywhere; "rows" of the video token matrix are (b * S + s).
+ *   - dropout masks are a pure function of (seed, site, row, col) (Philox4x32-10) so backward
+ *     entry points regenerate the forward's mask from the same (seed, site).
+ */
+#ifndef MMT_B200_H_
+#define MMT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMT_E_ARG (-1)      /* null pointer / bad enum */
+#define MMT_E_SHAPE (-2)    /* unsupported or inconsistent shape */
+#define MMT_E_ALIGN (-3)    /* pointer / stride alignment the kernel needs is not met */
+#define MMT_E_UNSUPPORTED (-4)
+
+int mmt_version(void);
+/* Copies the last error message of this thread's most recent failing call. */
+int mmt_last_error(char* buf, size_t len);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+int64_t mmt_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM:  C(m,n) = epilogue( alpha * sum_k A(m,k) * B(n,k) + bias[n] + add(m,n) )
+ * Replaces every torch addmm / matmul / bmm on the path: ReduceDim (model/model.py:723-726),
+ * Q/K/V, attention-output, intermediate and output dense layers (model/bert.py:137-143,186,218,
+ * 234), GatedEmbeddingUnit / ContextGating fc (model/model.py:698,746), moe_fc_txt (:277-279),
+ * the per-expert similarity matmuls (:823-824) and all of their autograd backward GEMMs.
+ *
+ * Operands are addressed by element strides so that transposed (wgrad / dgrad) and head-strided
+ * (attention) operands need no copies:
+ *   A(m,k) = A[m*a_ms + (k / a_kb)*a_kbs + (k % a_kb)*a_ks]      (a_kb == 0: A[m*a_ms + k*a_ks])
+ *   B(n,k) = B[n*b_ns + k*b_ks]
+ *   C(m,n) = C[(m / c_mb)*c_mbs + (m % c_mb)*c_ms + n]           (c_mb == 0: C[m*c_ms + n])
+ * `add` and `aux` use C's addressing.  Batched: z in [0,batch): z0 = z / batch_inner,
+ * z1 = z % batch_inner, operand X is offset by z0*x_bs0 + z1*x_bs1.
+ * Weight-gradient shaped problems (few output tiles, long K, dense un-batched C) are split along
+ * K across CTAs and reduced with fp32 atomics into a zeroed C.
+ * ------------------------------------------------------------------------------------------- */
+enum { MMT_EPI_NONE = 0,
+       MMT_EPI_GELU = 1,    /* aux <- pre-activation u, C <- gelu_erf(u)        (bert.py:218-219,53) */
+       MMT_EPI_DGELU = 2 }; /* C <- value * gelu_erf'(aux)   (autograd of bert.py:53)               */
+enum { MMT_PREC_FP32 = 0,   /* CUDA-core FMA, fp32 operands and accumulation (exact-order class)     */
+       MMT_PREC_TF32 = 1 }; /* tcgen05 kind::tf32 tensor-core tiles, TMA-fed, fp32 accumulate in TMEM */
+
+typedef struct mmt_gemm_desc {
+  int32_t M, N, K;
+  const float* A; int64_t a_ms, a_ks; int32_t a_kb; int64_t a_kbs;
+  const float* B; int64_t b_ns, b_ks;
+  float* C;       int64_t c_ms;       int32_t c_mb; int64_t c_mbs;
+  const float* bias;
+  const float* add;
+  float* aux;
+  int32_t epilogue;
+  float alpha;
+  int32_t batch, batch_inner;
+  int64_t a_bs0, a_bs1, b_bs0, b_bs1, c_bs0, c_bs1;
+  int64_t bias_bs;      /* bias of batch z starts at bias + z*bias_bs */
+  int32_t precision;
+} mmt_gemm_desc;
+
+int mmt_gemm(const mmt_gemm_desc* d, void* stream);
+
+/* out[n] (+)= sum_r X[(r / rb)*rbs + (r % rb)*ld + n]  (rb == 0: X[r*ld + n])
+ * -- bias gradients (autograd of every `+ b` above). */
+int mmt_colsum(const float* X, int64_t rows, int32_t n, int64_t ld, int32_t rb, int64_t rbs,
+               float* out, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Token assembly + BertEmbeddings  (model/model.py:485-567 + model/bert.py:87-105), one kernel.
+ * proj   [B*S, d]   raw ReduceDim GEMM outputs already sitting in their token slots (CLS rows are
+ *                   ignored); this kernel L2-normalises them (model.py:725, eps 1e-12), adds
+ *                   position/type embeddings, LayerNorms and applies dropout.
+ * ft,ind [M,B,T]    features_t / features_ind per expert (sorted expert order).
+ * type_idx [M]      int32 token-type id per expert (utils/util.py:154-247).
+ * Outputs: h [B*S,d]; mask [B*S] (1 = attend); pos_ids,type_ids [B*S] int32; inv_norm [B*S];
+ *          mean,rstd [B*S] (LayerNorm statistics, saved for backward).
+ * ------------------------------------------------------------------------------------------- */
+int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const int32_t* type_idx,
+                     const float* pos_emb, const float* type_emb, const float* gamma,
+                     const float* beta, int32_t B, int32_t M, int32_t T, int32_t d,
+                     int32_t max_pos, float eps, float p_drop, uint64_t seed, uint32_t site,
+                     float* h, float* mask, int32_t* pos_ids, int32_t* type_ids, float* inv_norm,
+                     float* mean, float* rstd, void* stream);
+/* Backward of the above: dh -> dproj (gradient w.r.t. the raw GEMM outputs, CLS rows zero) and
+ * ACCUMULATES into dpos_emb [max_pos,d], dtype_emb [type_vocab,d], dgamma, dbeta [d]. */
+int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
+                     const int32_t* type_ids, const float* inv_norm, const float* mean,
+                     const float* rstd, const float* pos_emb, const float* type_emb,
+                     const float* gamma, int32_t B, int32_t S, int32_t d, float p_drop,
+                     uint64_t seed, uint32_t site, float* dproj, float* dpos_emb,
+                     float* dtype_emb, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * y = LayerNorm(dropout(t) + r)   (BertSelfOutput / BertOutput, model/bert.py:186-188, 234-236)
+ * t is overwritten in place with z = dropout(t) + r (kept for backward).
+ * ------------------------------------------------------------------------------------------- */
+int mmt_res_ln_fwd(float* t_inout_z, const float* r, const float* gamma, const float* beta,
+                   int64_t rows, int32_t d, float eps, float p_drop, uint64_t seed, uint32_t site,
+                   float* y, float* mean, float* rstd, void* stream);
+/* dz = LN'(dy) (+ dy2 if non-null: a second upstream gradient added to dy first);
+ * dt = dropout-mask * dz (written only when p_drop > 0, else dt may alias / be NULL);
+ * ACCUMULATES dgamma, dbeta and dbias (= column sum of dt, the preceding dense layer's bias grad). */
+int mmt_res_ln_bwd(const float* dy, const float* dy2, const float* z, const float* mean,
+                   const float* rstd, const float* gamma, int64_t rows, int32_t d, float p_drop,
+                   uint64_t seed, uint32_t site, float* dz, float* dt, float* dgamma, float* dbeta,
+                   float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention probabilities over materialised scores (model/bert.py:147-164), fp32 path:
+ *   Psoft[b,h,i,:] = softmax(scores[b,h,i,:] * scale + (1 - mask[b,:]) * -10000)
+ *   Pdrop          = dropout(Psoft)            (written only when p_drop > 0)
+ * Rows are padded to `ld` (multiple of 4, >= S) floats; padded columns are written as 0.
+ * In-place (scores == Psoft) is allowed.  The tensor-core path fuses this into mmt_attention_*.
+ * ------------------------------------------------------------------------------------------- */
+int mmt_softmax_mask_fwd(const float* scores, const float* mask, int32_t B, int32_t H, int32_t S,
+                         int32_t ld, float scale, float p_drop, uint64_t seed, uint32_t site,
+                         float* Psoft, float* Pdrop, void* stream);
+/* In place on dP (= gradient w.r.t. Pdrop): dScores = scale * Psoft * (dA - sum_j dA*Psoft),
+ * dA = dropout-mask * dP. */
+int mmt_softmax_mask_bwd(float* dP_inout, const float* Psoft, int32_t B, int32_t H, int32_t S,
+                         int32_t ld, float scale, float p_drop, uint64_t seed, uint32_t site,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Expert read-out + L2 normalisation (model/model.py:583-587, 621-623):
+ * v[b,k,:] = normalize(h[b, 1 + k*(T+1), :]).  Backward scatters into dh (other rows zeroed).
+ * ------------------------------------------------------------------------------------------- */
+int mmt_readout_norm_fwd(const float* h, int32_t B, int32_t S, int32_t M, int32_t T, int32_t d,
+                         float* v, float* inv_norm, void* stream);
+int mmt_readout_norm_bwd(const float* dv, const float* v, const float* inv_norm, int32_t B,
+                         int32_t S, int32_t M, int32_t T, int32_t d, float* dh, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Text GatedEmbeddingUnit tail (model/model.py:697-702, 745-750, 624-625), all M experts at once.
+ * X [R, M*d] = fc(text), G [R, M*d] = cg.fc(X)  (the two GEMMs are mmt_gemm calls).
+ * y = normalize(normalize(X * sigmoid(BN(G))))  -> E [R, M, d]
+ * training != 0: BatchNorm1d uses batch statistics over the R rows (biased variance) and updates
+ * running_mean/var in place (momentum, unbiased variance); else uses the running statistics.
+ * Saves bn_mean, bn_rstd [M*d], inv_n1, inv_n2 [R*M] and Y [R, M*d] (pre-normalisation) for backward.
+ * ------------------------------------------------------------------------------------------- */
+int mmt_geu_gate_fwd(const float* X, const float* G, const float* bn_w, const float* bn_b,
+                     float* run_mean, float* run_var, int32_t R, int32_t M, int32_t d,
+                     int32_t training, float momentum, float bn_eps, float* E, float* Y,
+                     float* bn_mean, float* bn_rstd, float* inv_n1, float* inv_n2, void* stream);
+/* dE -> dX_direct [R,M*d] (through the x * sigmoid path) and dG [R,M*d] (through BatchNorm);
+ * ACCUMULATES dbn_w, dbn_b [M*d]. */
+int mmt_geu_gate_bwd(const float* dE, const float* X, const float* G, const float* Y,
+                     const float* E, const float* bn_w, const float* bn_b, const float* bn_mean,
+                     const float* bn_rstd, const float* inv_n1, const float* inv_n2, int32_t R,
+                     int32_t M, int32_t d, int32_t training, float* dX, float* dG, float* dbn_w,
+                     float* dbn_b, void* stream);
+
+/* Elementwise dropout out = mask * in / (1-p) (moe_txt_dropout, model/model.py:274). */
+int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, uint64_t seed,
+                uint32_t site, void* stream);
+/* Text mixture weights (model/model.py:276-281, 618): w = L1norm(softmax(logits)) over M <= 32. */
+int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, float* w, void* stream);
+int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, float* dlogits,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * sharded_cross_view_inner_product (model/model.py:789-837) given the per-expert dot products
+ * dots [M, Nq, Nv] (an mmt_gemm batch): sims[i,j] = sum_m (tw[i,m]*vw[j,m]/norm[i,j]) * dots[m,i,j],
+ * norm = sum_m tw*vw with exact zeros replaced by 1e-5.  caps > 1 and merge_avg != 0 averages the
+ * caps consecutive caption rows of each video (Nq = Nv*caps) into sims [Nv,Nv]; else sims [Nq,Nv].
+ * ------------------------------------------------------------------------------------------- */
+int mmt_sims_combine_fwd(const float* dots, const float* tw, const float* vw, int32_t Nq,
+                         int32_t Nv, int32_t M, int32_t caps, int32_t merge_avg, float* sims,
+                         void* stream);
+/* dsims -> ddots [M,Nq,Nv] and dtw [Nq,M] (vw carries no gradient: vid_wgh='none'). */
+int mmt_sims_combine_bwd(const float* dsims, const float* dots, const float* tw, const float* vw,
+                         int32_t Nq, int32_t Nv, int32_t M, int32_t caps, int32_t merge_avg,
+                         float* ddots, float* dtw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaxMarginRankingLoss (model/loss.py:38-65): loss = mean over the 2n(n-1) off-diagonal terms
+ * relu(m - x_ii + x_ij), relu(m - x_ii + x_ji)  (fix_norm != 0), or over all 2n^2 terms.
+ * loss is a device scalar; dx (may be NULL) receives d loss / d x  [n,n].
+ * HBM-bound streaming kernel: one read of x, one write of dx.
+ * ------------------------------------------------------------------------------------------- */
+int mmt_max_margin_fwd_bwd(const float* x, int32_t n, float margin, int32_t fix_norm, float* loss,
+                           float* dx, float* workspace /* >= 2n+2 floats, zeroed by the call */,
+                           void* stream);
+
+/* Fused Adam over a flat parameter buffer (torch.optim.Adam semantics, train.py:95-98):
+ * grad_scale multiplies the gradient first (1/world_size for replicated head gradients). */
+int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMT_B200_H_ */

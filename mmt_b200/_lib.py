@@ -1,0 +1,139 @@
+"""ctypes binding of libmmt_b200.so (the C ABI declared in include/mmt_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, this module
+raises.  PyTorch is only the owner of device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmt_b200.so")
+
+c_f = ctypes.c_float
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_u32 = ctypes.c_uint32
+c_u64 = ctypes.c_uint64
+c_p = ctypes.c_void_p
+
+EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
+PREC_FP32, PREC_TF32 = 0, 1
+
+
+class GemmDesc(ctypes.Structure):
+  _fields_ = [
+      ("M", c_i32), ("N", c_i32), ("K", c_i32),
+      ("A", c_p), ("a_ms", c_i64), ("a_ks", c_i64), ("a_kb", c_i32), ("a_kbs", c_i64),
+      ("B", c_p), ("b_ns", c_i64), ("b_ks", c_i64),
+      ("C", c_p), ("c_ms", c_i64), ("c_mb", c_i32), ("c_mbs", c_i64),
+      ("bias", c_p), ("add", c_p), ("aux", c_p),
+      ("epilogue", c_i32), ("alpha", c_f),
+      ("batch", c_i32), ("batch_inner", c_i32),
+      ("a_bs0", c_i64), ("a_bs1", c_i64), ("b_bs0", c_i64), ("b_bs1", c_i64),
+      ("c_bs0", c_i64), ("c_bs1", c_i64),
+      ("bias_bs", c_i64),
+      ("precision", c_i32),
+  ]
+
+
+# name -> (restype, argtypes); must list every symbol include/mmt_b200.h declares
+SIGNATURES = {
+    "mmt_version": (c_i32, []),
+    "mmt_last_error": (c_i32, [ctypes.c_char_p, ctypes.c_size_t]),
+    "mmt_launch_count": (c_i64, []),
+    "mmt_gemm": (c_i32, [ctypes.POINTER(GemmDesc), c_p]),
+    "mmt_colsum": (c_i32, [c_p, c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p]),
+    "mmt_embed_ln_fwd": (c_i32, [c_p] * 8 + [c_i32] * 5 + [c_f, c_f, c_u64, c_u32] + [c_p] * 7 + [c_p]),
+    "mmt_embed_ln_bwd": (c_i32, [c_p] * 10 + [c_i32] * 3 + [c_f, c_u64, c_u32] + [c_p] * 5 + [c_p]),
+    "mmt_res_ln_fwd": (c_i32, [c_p] * 4 + [c_i64, c_i32, c_f, c_f, c_u64, c_u32] + [c_p] * 3 + [c_p]),
+    "mmt_res_ln_bwd": (c_i32, [c_p] * 6 + [c_i64, c_i32, c_f, c_u64, c_u32] + [c_p] * 5 + [c_p]),
+    "mmt_softmax_mask_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p, c_p, c_p]),
+    "mmt_softmax_mask_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p]),
+    "mmt_readout_norm_fwd": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
+    "mmt_readout_norm_bwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
+    "mmt_geu_gate_fwd": (c_i32, [c_p] * 6 + [c_i32] * 4 + [c_f, c_f] + [c_p] * 6 + [c_p]),
+    "mmt_geu_gate_bwd": (c_i32, [c_p] * 11 + [c_i32] * 4 + [c_p] * 4 + [c_p]),
+    "mmt_dropout": (c_i32, [c_p, c_p, c_i64, c_i32, c_f, c_u64, c_u32, c_p]),
+    "mmt_moe_softmax_fwd": (c_i32, [c_p, c_i32, c_i32, c_p, c_p]),
+    "mmt_moe_softmax_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_p, c_p]),
+    "mmt_sims_combine_fwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
+    "mmt_sims_combine_bwd": (c_i32, [c_p] * 4 + [c_i32] * 5 + [c_p, c_p, c_p]),
+    "mmt_max_margin_fwd_bwd": (c_i32, [c_p, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p]),
+    "mmt_adam_step": (c_i32, [c_p] * 4 + [c_i64] + [c_f] * 5 + [c_i32, c_f, c_p]),
+}
+
+_lib = None
+
+
+def load():
+  """Loads libmmt_b200.so (building is __graft_entry__.build()'s job).  Raises if missing."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.isfile(LIB_PATH):
+    raise RuntimeError(
+        "mmt_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; "
+        "g.build()'` (or `make -C mmt_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, (res, args) in SIGNATURES.items():
+    fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+    fn.restype = res
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+def last_error():
+  buf = ctypes.create_string_buffer(512)
+  load().mmt_last_error(buf, 512)
+  return buf.value.decode(errors="replace")
+
+
+def check(rc, what):
+  if rc != 0:
+    raise RuntimeError("mmt_b200 %s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def stream_ptr():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, offset=0):
+  """Device pointer of a torch tensor (+ element offset); None -> NULL."""
+  if t is None:
+    return None
+  return t.data_ptr() + offset * t.element_size()
+
+
+def require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise RuntimeError("mmt_b200: expected CUDA tensors (no CPU fallback exists)")
+
+
+def launch_count():
+  return int(load().mmt_launch_count())
+
+
+def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_off=0, bias=None,
+         bias_off=0, add=None, add_off=0, aux=None, aux_off=0, epilogue=EPI_NONE, alpha=1.0,
+         a_kb=0, a_kbs=0, c_mb=0, c_mbs=0, batch=1, batch_inner=1, a_bs=(0, 0), b_bs=(0, 0),
+         c_bs=(0, 0), bias_bs=0, precision=PREC_FP32):
+  d = GemmDesc()
+  d.M, d.N, d.K = M, N, K
+  d.A, d.a_ms, d.a_ks, d.a_kb, d.a_kbs = ptr(A, a_off), a_ms, a_ks, a_kb, a_kbs
+  d.B, d.b_ns, d.b_ks = ptr(B, b_off), b_ns, b_ks
+  d.C, d.c_ms, d.c_mb, d.c_mbs = ptr(C, c_off), c_ms, c_mb, c_mbs
+  d.bias = ptr(bias, bias_off)
+  d.add = ptr(add, add_off)
+  d.aux = ptr(aux, aux_off)
+  d.epilogue, d.alpha = epilogue, alpha
+  d.batch, d.batch_inner = batch, batch_inner
+  d.a_bs0, d.a_bs1 = a_bs
+  d.b_bs0, d.b_bs1 = b_bs
+  d.c_bs0, d.c_bs1 = c_bs
+  d.bias_bs = bias_bs
+  d.precision = precision
+  check(load().mmt_gemm(ctypes.byref(d), stream_ptr()), "mmt_gemm")

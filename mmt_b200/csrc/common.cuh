@@ -1,0 +1,93 @@
+// Shared device/host helpers for the mmt_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mmt_b200.h"
+
+#include <atomic>
+
+namespace mmt {
+
+extern std::atomic<int64_t> g_launches;
+
+// ---- error plumbing (no exceptions cross the C ABI) -----------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_status(cudaError_t e, const char* what);
+
+#define MMT_ARG_CHECK(cond, code, ...)                 \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::mmt::set_error(__VA_ARGS__);                   \
+      return (code);                                   \
+    }                                                  \
+  } while (0)
+
+#define MMT_LAUNCH_CHECK(what)                                      \
+  do {                                                              \
+    ::mmt::g_launches.fetch_add(1, std::memory_order_relaxed);      \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) return ::mmt::cuda_status(e__, what);   \
+  } while (0)
+
+int num_sms();
+
+// ---- warp helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10, stateless: (seed, 4x32 counter) -> 4x32 random bits ------------------------
+// Dropout masks are a pure function of (seed, site, row, col/4) so that the backward kernels
+// regenerate exactly the mask the forward used without storing it.
+struct Philox {
+  static __device__ __forceinline__ uint4 gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2,
+                                              uint32_t c3) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// keep-mask scale for 4 consecutive columns [col4*4, col4*4+4) of `row` at dropout `site`.
+// Returns 0 or 1/(1-p) per element.  p == 0 -> all ones (callers skip the call).
+__device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, uint32_t row,
+                                                 uint32_t col4, float p, float inv_keep) {
+  uint4 r = Philox::gen(seed, row, col4, site, 0x6d6d7462u);
+  // keep iff u >= p with u uniform in [0,1): compare on the 32-bit integer
+  uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
+  float4 o;
+  o.x = r.x >= thr ? inv_keep : 0.f;
+  o.y = r.y >= thr ? inv_keep : 0.f;
+  o.z = r.z >= thr ? inv_keep : 0.f;
+  o.w = r.w >= thr ? inv_keep : 0.f;
+  return o;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // model/bert.py:53: x * 0.5 * (1 + erf(x / sqrt(2)))
+  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+}  // namespace mmt

@@ -1,0 +1,180 @@
+// fp32 CUDA-core GEMM with generic operand strides (MMT_PREC_FP32).
+//
+// Used for (a) the exact-fp32 mode of every linear layer (parity to ~1e-6 against the oracle),
+// (b) permanently for the small / oddly-shaped products of the text head and the similarity
+// matrix, where "ranking indices bit-exact at the similarity boundary" needs true fp32 FMAs
+// (SURVEY.md §7 hard parts), and (c) as the on-GPU cross-check of the tcgen05 path in tests.
+//
+// 128x128x16 tiles, 256 threads, 8x8 register micro-tile per thread, register-staged double
+// buffering.  Operands are fetched with element strides, so no transposes are ever materialised.
+#include "common.cuh"
+
+namespace mmt {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
+constexpr int PAD = 4;
+
+struct GemmArgs {
+  mmt_gemm_desc d;
+  int split_k;     // CTAs along K per output tile (atomic reduction into a zeroed C when > 1)
+  int k_chunk;     // K elements per split, multiple of BK
+};
+
+__device__ __forceinline__ int64_t a_off(const mmt_gemm_desc& d, int m, int k) {
+  if (d.a_kb > 0) return (int64_t)m * d.a_ms + (int64_t)(k / d.a_kb) * d.a_kbs + (int64_t)(k % d.a_kb) * d.a_ks;
+  return (int64_t)m * d.a_ms + (int64_t)k * d.a_ks;
+}
+__device__ __forceinline__ int64_t c_off(const mmt_gemm_desc& d, int m) {
+  if (d.c_mb > 0) return (int64_t)(m / d.c_mb) * d.c_mbs + (int64_t)(m % d.c_mb) * d.c_ms;
+  return (int64_t)m * d.c_ms;
+}
+
+// A_KFAST: consecutive threads walk k (operand contiguous along k); else they walk m / n.
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(NT) sgemm_kernel(const GemmArgs args) {
+  const mmt_gemm_desc& d = args.d;
+  __shared__ float As[2][BK][BM + PAD];
+  __shared__ float Bs[2][BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int z = blockIdx.z / args.split_k;
+  const int ksplit = blockIdx.z % args.split_k;
+  const int k_begin = ksplit * args.k_chunk;
+  const int k_end = min(d.K, k_begin + args.k_chunk);
+  const int z0 = z / d.batch_inner, z1 = z % d.batch_inner;
+  const float* __restrict__ A = d.A + z0 * d.a_bs0 + z1 * d.a_bs1;
+  const float* __restrict__ B = d.B + z0 * d.b_bs0 + z1 * d.b_bs1;
+  const int64_t c_base = z0 * d.c_bs0 + z1 * d.c_bs1;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  // loader mapping: 128x16 elements per operand per tile = 2048 / 256 threads = 8 each
+  float ra[8], rb[8];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int e = tid + i * NT;
+      int mm, kk;
+      if (A_KFAST) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      int m = m0 + mm, k = k0 + kk;
+      ra[i] = (m < d.M && k < k_end) ? __ldg(A + a_off(d, m, k)) : 0.f;
+      int nn;
+      if (B_KFAST) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      int n = n0 + nn;
+      k = k0 + kk;
+      rb[i] = (n < d.N && k < k_end) ? __ldg(B + (int64_t)n * d.b_ns + (int64_t)k * d.b_ks) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int e = tid + i * NT;
+      int mm, kk, nn;
+      if (A_KFAST) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      As[buf][kk][mm] = ra[i];
+      if (B_KFAST) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      Bs[buf][kk][nn] = rb[i];
+    }
+  };
+
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = (k_end - k_begin + BK - 1) / BK;
+  if (nk <= 0) return;
+  load_tile(k_begin);
+  store_tile(0);
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) load_tile(k_begin + (t + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < nk) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= d.M) continue;
+    const int64_t row = c_base + c_off(d, m);
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int nb = n0 + jh * 64 + tx * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = nb + j;
+        if (n >= d.N) continue;
+        float v = acc[i][jh * 4 + j] * d.alpha;
+        if (args.split_k > 1) {
+          if (ksplit == 0) {
+            if (d.bias) v += __ldg(d.bias + z * d.bias_bs + n);
+            if (d.add) v += d.add[row + n];
+          }
+          atomicAdd(d.C + row + n, v);
+          continue;
+        }
+        if (d.bias) v += __ldg(d.bias + z * d.bias_bs + n);
+        if (d.add) v += d.add[row + n];
+        if (d.epilogue == MMT_EPI_GELU) {
+          d.aux[row + n] = v;
+          v = gelu_erf(v);
+        } else if (d.epilogue == MMT_EPI_DGELU) {
+          v *= dgelu_erf(d.aux[row + n]);
+        }
+        d.C[row + n] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
+  GemmArgs args{d, 1, ((d.K + BK - 1) / BK) * BK};
+  const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
+  // weight-gradient shape: few output tiles, long K, dense un-batched C that is not also `add`
+  if (d.batch == 1 && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
+      d.add != d.C && tiles * 2 <= num_sms() && d.K >= 32 * BK) {
+    int split = (2 * num_sms() + tiles - 1) / tiles;
+    const int max_split = d.K / (8 * BK);
+    if (split > max_split) split = max_split;
+    if (split > 1) {
+      args.k_chunk = (((d.K + split - 1) / split + BK - 1) / BK) * BK;
+      args.split_k = (d.K + args.k_chunk - 1) / args.k_chunk;
+      cudaError_t e = cudaMemsetAsync(d.C, 0, sizeof(float) * (size_t)d.M * d.N, stream);
+      if (e != cudaSuccess) return cuda_status(e, "sgemm split-K memset");
+    }
+  }
+  dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch * args.split_k);
+  const bool a_kfast = (d.a_ks == 1);
+  const bool b_kfast = (d.b_ks == 1);
+  if (a_kfast && b_kfast) sgemm_kernel<true, true><<<grid, NT, 0, stream>>>(args);
+  else if (a_kfast) sgemm_kernel<true, false><<<grid, NT, 0, stream>>>(args);
+  else if (b_kfast) sgemm_kernel<false, true><<<grid, NT, 0, stream>>>(args);
+  else sgemm_kernel<false, false><<<grid, NT, 0, stream>>>(args);
+  MMT_LAUNCH_CHECK("sgemm_kernel");
+  return 0;
+}
+
+}  // namespace mmt

@@ -1,0 +1,634 @@
+// HBM-bound row kernels of the video encoder: token assembly + BertEmbeddings, residual +
+// LayerNorm, masked softmax, expert read-out, bias-gradient column sums, dropout.
+//
+// Layout: one warp per row of d = 128*VEC floats; lane l owns the float4s at columns
+// 4*(l + 32*v), v < VEC, so every warp-wide access is a fully coalesced 512 B segment and all
+// row reductions are warp shuffles.  Column reductions (dgamma/dbeta/dbias) are kept in
+// registers across a grid-stride loop over rows, reduced across the block's warps through shared
+// memory and flushed with one vector atomic per lane per block.
+#include "rowvec.cuh"
+
+namespace mmt {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Token assembly + BertEmbeddings forward (model/model.py:485-567, model/bert.py:87-105)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
+    const float* __restrict__ proj, const float* __restrict__ ft, const float* __restrict__ ind,
+    const int32_t* __restrict__ type_idx, const float* __restrict__ pos_emb,
+    const float* __restrict__ type_emb, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int B, int M, int T, int max_pos, float eps, float p_drop,
+    uint64_t seed, uint32_t site, float* __restrict__ h, float* __restrict__ mask,
+    int32_t* __restrict__ pos_ids, int32_t* __restrict__ type_ids, float* __restrict__ inv_norm,
+    float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  constexpr int d = 128 * VEC;
+  const int S = 1 + M * (T + 1);
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * S;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float4 g[VEC], bt[VEC];
+  load_row<VEC>(gamma, lane, g);
+  load_row<VEC>(beta, lane, bt);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
+       r += (int64_t)gridDim.x * WARPS) {
+    const int b = (int)(r / S), s = (int)(r % S);
+    int type = 0, pos = 0;
+    float mk = 1.f, invn = 0.f;
+    float4 e[VEC];
+    if (s == 0) {                                        // [CLS]: model.py:496-504
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const int k = (s - 1) / (T + 1), j = (s - 1) % (T + 1);
+      type = type_idx[k];
+      const float* indp = ind + ((int64_t)k * B + b) * T;
+      if (j == 0) {                                      // [AGG]: model.py:526-541, 329-330
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, indp[t]);
+        mx = warp_max(mx);
+        mk = (float)(long long)mx;
+      } else {                                           // temporal token: model.py:543-558
+        float tv = ft[((int64_t)k * B + b) * T + (j - 1)];
+        tv = fminf(fmaxf(tv, 0.f), (float)(max_pos - 1));   // clamp_ (model.py:516-518)
+        pos = (int)tv;                                       // .long(): truncation
+        mk = (float)(long long)indp[j - 1];
+      }
+      load_row<VEC>(proj + r * d, lane, e);
+      float ss = row_dot<VEC>(e, e);
+      invn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize eps (model.py:725)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) F4_OP(e[i], e[i].x * invn, e[i].y * invn, e[i].z * invn, e[i].w * invn);
+    }
+    float4 pe[VEC], te[VEC];
+    load_row<VEC>(pos_emb + (int64_t)pos * d, lane, pe);
+    load_row<VEC>(type_emb + (int64_t)type * d, lane, te);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)                        // bert.py:99: pos + type + features
+      F4_OP(e[i], (pe[i].x + te[i].x) + e[i].x, (pe[i].y + te[i].y) + e[i].y,
+            (pe[i].z + te[i].z) + e[i].z, (pe[i].w + te[i].w) + e[i].w);
+    float mean, rstd;
+    ln_stats<VEC>(e, d, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      F4_OP(e[i], (e[i].x - mean) * rstd * g[i].x + bt[i].x, (e[i].y - mean) * rstd * g[i].y + bt[i].y,
+            (e[i].z - mean) * rstd * g[i].z + bt[i].z, (e[i].w - mean) * rstd * g[i].w + bt[i].w);
+      if (p_drop > 0.f) {
+        float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
+        F4_OP(e[i], e[i].x * sc.x, e[i].y * sc.y, e[i].z * sc.z, e[i].w * sc.w);
+      }
+    }
+    store_row<VEC>(h + r * d, lane, e);
+    if (lane == 0) {
+      mask[r] = mk; pos_ids[r] = pos; type_ids[r] = type; inv_norm[r] = invn;
+      mean_o[r] = mean; rstd_o[r] = rstd;
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
+    const float* __restrict__ dh, const float* __restrict__ proj,
+    const int32_t* __restrict__ pos_ids, const int32_t* __restrict__ type_ids,
+    const float* __restrict__ inv_norm, const float* __restrict__ mean_i,
+    const float* __restrict__ rstd_i, const float* __restrict__ pos_emb,
+    const float* __restrict__ type_emb, const float* __restrict__ gamma, int B, int S,
+    float p_drop, uint64_t seed, uint32_t site, float* __restrict__ dproj,
+    float* __restrict__ dpos_emb, float* __restrict__ dtype_emb, float* __restrict__ dgamma,
+    float* __restrict__ dbeta) {
+  constexpr int d = 128 * VEC;
+  __shared__ float4 red[WARPS * VEC * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t rows = (int64_t)B * S;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float4 g[VEC], ag[VEC], ab[VEC];
+  load_row<VEC>(gamma, lane, g);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
+    const int s = (int)(r % S);
+    const int pos = pos_ids[r], type = type_ids[r];
+    const float invn = inv_norm[r], mean = mean_i[r], rstd = rstd_i[r];
+    float4 gy[VEC], f[VEC], xh[VEC], pe[VEC], te[VEC];
+    load_row<VEC>(dh + r * d, lane, gy);
+    if (p_drop > 0.f) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
+        F4_OP(gy[i], gy[i].x * sc.x, gy[i].y * sc.y, gy[i].z * sc.z, gy[i].w * sc.w);
+      }
+    }
+    if (s == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      load_row<VEC>(proj + r * d, lane, f);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) F4_OP(f[i], f[i].x * invn, f[i].y * invn, f[i].z * invn, f[i].w * invn);
+    }
+    load_row<VEC>(pos_emb + (int64_t)pos * d, lane, pe);
+    load_row<VEC>(type_emb + (int64_t)type * d, lane, te);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      F4_OP(xh[i], (((pe[i].x + te[i].x) + f[i].x) - mean) * rstd,
+            (((pe[i].y + te[i].y) + f[i].y) - mean) * rstd,
+            (((pe[i].z + te[i].z) + f[i].z) - mean) * rstd,
+            (((pe[i].w + te[i].w) + f[i].w) - mean) * rstd);
+      ag[i].x += gy[i].x * xh[i].x; ag[i].y += gy[i].y * xh[i].y;
+      ag[i].z += gy[i].z * xh[i].z; ag[i].w += gy[i].w * xh[i].w;
+      ab[i].x += gy[i].x; ab[i].y += gy[i].y; ab[i].z += gy[i].z; ab[i].w += gy[i].w;
+      F4_OP(gy[i], gy[i].x * g[i].x, gy[i].y * g[i].y, gy[i].z * g[i].z, gy[i].w * g[i].w);  // d xhat
+    }
+    const float m1 = row_sum<VEC>(gy) / d;
+    const float m2 = row_dot<VEC>(gy, xh) / d;
+    float4 de[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      F4_OP(de[i], rstd * (gy[i].x - m1 - xh[i].x * m2), rstd * (gy[i].y - m1 - xh[i].y * m2),
+            rstd * (gy[i].z - m1 - xh[i].z * m2), rstd * (gy[i].w - m1 - xh[i].w * m2));
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      atomic_add4(dpos_emb + (int64_t)pos * d + 4 * (lane + 32 * i), de[i]);
+      atomic_add4(dtype_emb + (int64_t)type * d + 4 * (lane + 32 * i), de[i]);
+    }
+    if (s == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) de[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (invn < 1e12f) {                           // normalize backward: (I - f f^T) de / ||y||
+      const float dot = row_dot<VEC>(f, de);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        F4_OP(de[i], invn * (de[i].x - f[i].x * dot), invn * (de[i].y - f[i].y * dot),
+              invn * (de[i].z - f[i].z * dot), invn * (de[i].w - f[i].w * dot));
+    } else {                                             // ||y|| <= eps: y / eps is linear
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) F4_OP(de[i], de[i].x * invn, de[i].y * invn, de[i].z * invn, de[i].w * invn);
+    }
+    store_row<VEC>(dproj + r * d, lane, de);
+  }
+  flush_cols<VEC>(ag, dgamma, lane, warp, red);
+  flush_cols<VEC>(ab, dbeta, lane, warp, red);
+}
+
+// ------------------------------------------------------------------------------------------
+// y = LN(dropout(t) + r)   (model/bert.py:186-188, 234-236)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) res_ln_fwd_kernel(
+    float* __restrict__ t, const float* __restrict__ res, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int64_t rows, float eps, float p_drop, uint64_t seed,
+    uint32_t site, float* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  constexpr int d = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float4 g[VEC], bt[VEC];
+  load_row<VEC>(gamma, lane, g);
+  load_row<VEC>(beta, lane, bt);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
+       r += (int64_t)gridDim.x * WARPS) {
+    float4 z[VEC], rr[VEC];
+    load_row<VEC>(t + r * d, lane, z);
+    load_row<VEC>(res + r * d, lane, rr);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (p_drop > 0.f) {
+        float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
+        F4_OP(z[i], z[i].x * sc.x, z[i].y * sc.y, z[i].z * sc.z, z[i].w * sc.w);
+      }
+      F4_OP(z[i], z[i].x + rr[i].x, z[i].y + rr[i].y, z[i].z + rr[i].z, z[i].w + rr[i].w);
+    }
+    store_row<VEC>(t + r * d, lane, z);
+    float mean, rstd;
+    ln_stats<VEC>(z, d, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      F4_OP(z[i], (z[i].x - mean) * rstd * g[i].x + bt[i].x, (z[i].y - mean) * rstd * g[i].y + bt[i].y,
+            (z[i].z - mean) * rstd * g[i].z + bt[i].z, (z[i].w - mean) * rstd * g[i].w + bt[i].w);
+    store_row<VEC>(y + r * d, lane, z);
+    if (lane == 0) { mean_o[r] = mean; rstd_o[r] = rstd; }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
+    const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ z,
+    const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
+    const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site,
+    float* __restrict__ dz, float* __restrict__ dt, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ dbias) {
+  constexpr int d = 128 * VEC;
+  __shared__ float4 red[WARPS * VEC * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float4 g[VEC], ag[VEC], ab[VEC], abias[VEC];
+  load_row<VEC>(gamma, lane, g);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = abias[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
+    const float mean = mean_i[r], rstd = rstd_i[r];
+    float4 gy[VEC], xh[VEC];
+    load_row<VEC>(dy + r * d, lane, gy);
+    if (dy2 != nullptr) {
+      float4 g2[VEC];
+      load_row<VEC>(dy2 + r * d, lane, g2);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) F4_OP(gy[i], gy[i].x + g2[i].x, gy[i].y + g2[i].y, gy[i].z + g2[i].z, gy[i].w + g2[i].w);
+    }
+    load_row<VEC>(z + r * d, lane, xh);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      F4_OP(xh[i], (xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
+      ag[i].x += gy[i].x * xh[i].x; ag[i].y += gy[i].y * xh[i].y;
+      ag[i].z += gy[i].z * xh[i].z; ag[i].w += gy[i].w * xh[i].w;
+      ab[i].x += gy[i].x; ab[i].y += gy[i].y; ab[i].z += gy[i].z; ab[i].w += gy[i].w;
+      F4_OP(gy[i], gy[i].x * g[i].x, gy[i].y * g[i].y, gy[i].z * g[i].z, gy[i].w * g[i].w);
+    }
+    const float m1 = row_sum<VEC>(gy) / d;
+    const float m2 = row_dot<VEC>(gy, xh) / d;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      F4_OP(gy[i], rstd * (gy[i].x - m1 - xh[i].x * m2), rstd * (gy[i].y - m1 - xh[i].y * m2),
+            rstd * (gy[i].z - m1 - xh[i].z * m2), rstd * (gy[i].w - m1 - xh[i].w * m2));
+    store_row<VEC>(dz + r * d, lane, gy);
+    if (p_drop > 0.f) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
+        F4_OP(gy[i], gy[i].x * sc.x, gy[i].y * sc.y, gy[i].z * sc.z, gy[i].w * sc.w);
+      }
+      store_row<VEC>(dt + r * d, lane, gy);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      abias[i].x += gy[i].x; abias[i].y += gy[i].y; abias[i].z += gy[i].z; abias[i].w += gy[i].w;
+    }
+  }
+  flush_cols<VEC>(ag, dgamma, lane, warp, red);
+  flush_cols<VEC>(ab, dbeta, lane, warp, red);
+  flush_cols<VEC>(abias, dbias, lane, warp, red);
+}
+
+// ------------------------------------------------------------------------------------------
+// masked softmax over materialised scores (model/bert.py:147-164), one warp per (b,h,i) row
+// ------------------------------------------------------------------------------------------
+constexpr int SM_MAXC = 4;   // float4 chunks per lane -> S <= 512
+
+__global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
+    const float* __restrict__ scores, const float* __restrict__ mask, int B, int H, int S, int ld,
+    float scale, float p_drop, uint64_t seed, uint32_t site, float* __restrict__ Psoft,
+    float* __restrict__ Pdrop) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)B * H * S;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
+       r += (int64_t)gridDim.x * WARPS) {
+    const int b = (int)(r / ((int64_t)H * S));
+    const float* __restrict__ mrow = mask + (int64_t)b * S;
+    float4 x[SM_MAXC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < SM_MAXC; ++c) {
+      const int j = 4 * (lane + 32 * c);
+      if (j < ld) {
+        float4 v = *reinterpret_cast<const float4*>(scores + r * ld + j);
+        float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // bert.py:149-152: scores / sqrt(dh) + (1 - mask) * -10000
+          pv[q] = (j + q < S) ? pv[q] * scale + (1.0f - mrow[j + q]) * -10000.0f : -INFINITY;
+          mx = fmaxf(mx, pv[q]);
+        }
+        x[c] = v;
+      } else {
+        x[c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < SM_MAXC; ++c) {
+      F4_OP(x[c], expf(x[c].x - mx), expf(x[c].y - mx), expf(x[c].z - mx), expf(x[c].w - mx));
+      sum += (x[c].x + x[c].y) + (x[c].z + x[c].w);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c = 0; c < SM_MAXC; ++c) {
+      const int j = 4 * (lane + 32 * c);
+      if (j < ld) {
+        float4 p;
+        F4_OP(p, x[c].x * inv, x[c].y * inv, x[c].z * inv, x[c].w * inv);
+        *reinterpret_cast<float4*>(Psoft + r * ld + j) = p;
+        if (p_drop > 0.f) {
+          float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
+          F4_OP(p, p.x * sc.x, p.y * sc.y, p.z * sc.z, p.w * sc.w);
+          *reinterpret_cast<float4*>(Pdrop + r * ld + j) = p;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) softmax_bwd_kernel(
+    float* __restrict__ dP, const float* __restrict__ Psoft, int64_t rows, int S, int ld,
+    float scale, float p_drop, uint64_t seed, uint32_t site) {
+  const int lane = threadIdx.x & 31;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
+       r += (int64_t)gridDim.x * WARPS) {
+    float4 da[SM_MAXC], a[SM_MAXC];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < SM_MAXC; ++c) {
+      const int j = 4 * (lane + 32 * c);
+      if (j < ld) {
+        da[c] = *reinterpret_cast<const float4*>(dP + r * ld + j);
+        a[c] = *reinterpret_cast<const float4*>(Psoft + r * ld + j);
+        if (p_drop > 0.f) {
+          float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
+          F4_OP(da[c], da[c].x * sc.x, da[c].y * sc.y, da[c].z * sc.z, da[c].w * sc.w);
+        }
+        float* pa = reinterpret_cast<float*>(&a[c]);
+        float* pd = reinterpret_cast<float*>(&da[c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j + q >= S) { pa[q] = 0.f; pd[q] = 0.f; }
+          dot += pa[q] * pd[q];
+        }
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int c = 0; c < SM_MAXC; ++c) {
+      const int j = 4 * (lane + 32 * c);
+      if (j < ld) {
+        float4 o;
+        F4_OP(o, a[c].x * (da[c].x - dot) * scale, a[c].y * (da[c].y - dot) * scale,
+              a[c].z * (da[c].z - dot) * scale, a[c].w * (da[c].w - dot) * scale);
+        *reinterpret_cast<float4*>(dP + r * ld + j) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// expert read-out + L2 normalise (model/model.py:583-587, 621-623)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) readout_fwd_kernel(
+    const float* __restrict__ h, int B, int S, int M, int T, float* __restrict__ v,
+    float* __restrict__ inv_norm) {
+  constexpr int d = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= B * M) return;
+  const int b = r / M, k = r % M;
+  float4 x[VEC];
+  load_row<VEC>(h + ((int64_t)b * S + 1 + (int64_t)k * (T + 1)) * d, lane, x);
+  const float invn = 1.0f / fmaxf(sqrtf(row_dot<VEC>(x, x)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) F4_OP(x[i], x[i].x * invn, x[i].y * invn, x[i].z * invn, x[i].w * invn);
+  store_row<VEC>(v + (int64_t)r * d, lane, x);
+  if (lane == 0) inv_norm[r] = invn;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) readout_bwd_kernel(
+    const float* __restrict__ dv, const float* __restrict__ v, const float* __restrict__ inv_norm,
+    int B, int S, int M, int T, float* __restrict__ dh) {
+  constexpr int d = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (r >= B * M) return;
+  const int b = r / M, k = r % M;
+  float4 g[VEC], f[VEC];
+  load_row<VEC>(dv + (int64_t)r * d, lane, g);
+  load_row<VEC>(v + (int64_t)r * d, lane, f);
+  const float invn = inv_norm[r];
+  if (invn < 1e12f) {
+    const float dot = row_dot<VEC>(f, g);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      F4_OP(g[i], invn * (g[i].x - f[i].x * dot), invn * (g[i].y - f[i].y * dot),
+            invn * (g[i].z - f[i].z * dot), invn * (g[i].w - f[i].w * dot));
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) F4_OP(g[i], g[i].x * invn, g[i].y * invn, g[i].z * invn, g[i].w * invn);
+  }
+  store_row<VEC>(dh + ((int64_t)b * S + 1 + (int64_t)k * (T + 1)) * d, lane, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients) and elementwise dropout
+// ------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t rows, int n,
+                                                     int64_t ld, int rb, int64_t rbs,
+                                                     float* __restrict__ out) {
+  __shared__ float4 red[8][32];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;        // float4 column index
+  const int ty = threadIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < n) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+      const float* p = X + (rb > 0 ? (r / rb) * rbs + (r % rb) * ld : r * ld) + 4 * c4;
+      if (VEC4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      } else {
+        acc.x += p[0];
+        if (4 * c4 + 1 < n) acc.y += p[1];
+        if (4 * c4 + 2 < n) acc.z += p[2];
+        if (4 * c4 + 3 < n) acc.w += p[3];
+      }
+    }
+  }
+  red[ty][threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0 && c4 * 4 < n) {
+    for (int w = 1; w < 8; ++w) {
+      float4 t = red[w][threadIdx.x];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (VEC4) atomic_add4(out + 4 * c4, acc);
+    else {
+      atomicAdd(out + 4 * c4, acc.x);
+      if (4 * c4 + 1 < n) atomicAdd(out + 4 * c4 + 1, acc.y);
+      if (4 * c4 + 2 < n) atomicAdd(out + 4 * c4 + 2, acc.z);
+      if (4 * c4 + 3 < n) atomicAdd(out + 4 * c4 + 3, acc.w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ in,
+                                                      float* __restrict__ out, int64_t rows, int n4,
+                                                      float p, uint64_t seed, uint32_t site) {
+  const float inv_keep = 1.f / (1.f - p);
+  const int64_t total = rows * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n4;
+    const int c4 = (int)(i % n4);
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    float4 sc = dropout_scale4(seed, site, (uint32_t)r, c4, p, inv_keep);
+    F4_OP(v, v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+}  // namespace
+}  // namespace mmt
+
+using namespace mmt;
+
+extern "C" {
+
+int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const int32_t* type_idx,
+                     const float* pos_emb, const float* type_emb, const float* gamma,
+                     const float* beta, int32_t B, int32_t M, int32_t T, int32_t d,
+                     int32_t max_pos, float eps, float p_drop, uint64_t seed, uint32_t site,
+                     float* h, float* mask, int32_t* pos_ids, int32_t* type_ids, float* inv_norm,
+                     float* mean, float* rstd, void* stream) {
+  MMT_ARG_CHECK(proj && ft && ind && type_idx && pos_emb && type_emb && gamma && beta && h && mask &&
+                pos_ids && type_ids && inv_norm && mean && rstd, MMT_E_ARG, "mmt_embed_ln_fwd: null pointer");
+  MMT_ARG_CHECK(B > 0 && M > 0 && T > 0 && max_pos > 0, MMT_E_SHAPE, "mmt_embed_ln_fwd: bad shape B=%d M=%d T=%d", B, M, T);
+  CHECK_D(d); CHECK_P(p_drop);
+  const int64_t rows = (int64_t)B * (1 + M * (T + 1));
+  DISPATCH_VEC(d, (embed_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+      proj, ft, ind, type_idx, pos_emb, type_emb, gamma, beta, B, M, T, max_pos, eps, p_drop, seed,
+      site, h, mask, pos_ids, type_ids, inv_norm, mean, rstd)));
+  MMT_LAUNCH_CHECK("embed_ln_fwd");
+  return 0;
+}
+
+int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
+                     const int32_t* type_ids, const float* inv_norm, const float* mean,
+                     const float* rstd, const float* pos_emb, const float* type_emb,
+                     const float* gamma, int32_t B, int32_t S, int32_t d, float p_drop,
+                     uint64_t seed, uint32_t site, float* dproj, float* dpos_emb,
+                     float* dtype_emb, float* dgamma, float* dbeta, void* stream) {
+  MMT_ARG_CHECK(dh && proj && pos_ids && type_ids && inv_norm && mean && rstd && pos_emb && type_emb &&
+                gamma && dproj && dpos_emb && dtype_emb && dgamma && dbeta, MMT_E_ARG, "mmt_embed_ln_bwd: null pointer");
+  CHECK_D(d); CHECK_P(p_drop);
+  const int64_t rows = (int64_t)B * S;
+  int grid = row_grid(rows);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  DISPATCH_VEC(d, (embed_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+      dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, S, p_drop,
+      seed, site, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
+  MMT_LAUNCH_CHECK("embed_ln_bwd");
+  return 0;
+}
+
+int mmt_res_ln_fwd(float* t, const float* r, const float* gamma, const float* beta, int64_t rows,
+                   int32_t d, float eps, float p_drop, uint64_t seed, uint32_t site, float* y,
+                   float* mean, float* rstd, void* stream) {
+  MMT_ARG_CHECK(t && r && gamma && beta && y && mean && rstd, MMT_E_ARG, "mmt_res_ln_fwd: null pointer");
+  CHECK_D(d); CHECK_P(p_drop);
+  if (rows == 0) return 0;
+  DISPATCH_VEC(d, (res_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+      t, r, gamma, beta, rows, eps, p_drop, seed, site, y, mean, rstd)));
+  MMT_LAUNCH_CHECK("res_ln_fwd");
+  return 0;
+}
+
+int mmt_res_ln_bwd(const float* dy, const float* dy2, const float* z, const float* mean,
+                   const float* rstd, const float* gamma, int64_t rows, int32_t d, float p_drop,
+                   uint64_t seed, uint32_t site, float* dz, float* dt, float* dgamma, float* dbeta,
+                   float* dbias, void* stream) {
+  MMT_ARG_CHECK(dy && z && mean && rstd && gamma && dz && dgamma && dbeta, MMT_E_ARG, "mmt_res_ln_bwd: null pointer");
+  MMT_ARG_CHECK(p_drop == 0.f || dt != nullptr, MMT_E_ARG, "mmt_res_ln_bwd: dt required when p_drop > 0");
+  CHECK_D(d); CHECK_P(p_drop);
+  if (rows == 0) return 0;
+  int grid = row_grid(rows);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  DISPATCH_VEC(d, (res_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, dz, dt, dgamma, dbeta, dbias)));
+  MMT_LAUNCH_CHECK("res_ln_bwd");
+  return 0;
+}
+
+int mmt_softmax_mask_fwd(const float* scores, const float* mask, int32_t B, int32_t H, int32_t S,
+                         int32_t ld, float scale, float p_drop, uint64_t seed, uint32_t site,
+                         float* Psoft, float* Pdrop, void* stream) {
+  MMT_ARG_CHECK(scores && mask && Psoft, MMT_E_ARG, "mmt_softmax_mask_fwd: null pointer");
+  MMT_ARG_CHECK(p_drop == 0.f || Pdrop != nullptr, MMT_E_ARG, "mmt_softmax_mask_fwd: Pdrop required when p_drop > 0");
+  MMT_ARG_CHECK(S > 0 && S <= 128 * SM_MAXC && ld >= S && ld % 4 == 0 && ld <= 128 * SM_MAXC, MMT_E_SHAPE,
+                "mmt_softmax_mask_fwd: S=%d ld=%d unsupported (S <= %d, ld %% 4 == 0)", S, ld, 128 * SM_MAXC);
+  CHECK_P(p_drop);
+  softmax_fwd_kernel<<<row_grid((int64_t)B * H * S), WARPS * 32, 0, (cudaStream_t)stream>>>(
+      scores, mask, B, H, S, ld, scale, p_drop, seed, site, Psoft, Pdrop);
+  MMT_LAUNCH_CHECK("softmax_fwd");
+  return 0;
+}
+
+int mmt_softmax_mask_bwd(float* dP, const float* Psoft, int32_t B, int32_t H, int32_t S, int32_t ld,
+                         float scale, float p_drop, uint64_t seed, uint32_t site, void* stream) {
+  MMT_ARG_CHECK(dP && Psoft, MMT_E_ARG, "mmt_softmax_mask_bwd: null pointer");
+  MMT_ARG_CHECK(S > 0 && ld >= S && ld % 4 == 0 && ld <= 128 * SM_MAXC, MMT_E_SHAPE, "mmt_softmax_mask_bwd: S=%d ld=%d unsupported", S, ld);
+  CHECK_P(p_drop);
+  const int64_t rows = (int64_t)B * H * S;
+  softmax_bwd_kernel<<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(dP, Psoft, rows, S, ld, scale, p_drop, seed, site);
+  MMT_LAUNCH_CHECK("softmax_bwd");
+  return 0;
+}
+
+int mmt_readout_norm_fwd(const float* h, int32_t B, int32_t S, int32_t M, int32_t T, int32_t d,
+                         float* v, float* inv_norm, void* stream) {
+  MMT_ARG_CHECK(h && v && inv_norm, MMT_E_ARG, "mmt_readout_norm_fwd: null pointer");
+  MMT_ARG_CHECK(S == 1 + M * (T + 1), MMT_E_SHAPE, "mmt_readout_norm_fwd: S=%d != 1+M*(T+1)", S);
+  CHECK_D(d);
+  DISPATCH_VEC(d, (readout_fwd_kernel<V><<<(B * M + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(h, B, S, M, T, v, inv_norm)));
+  MMT_LAUNCH_CHECK("readout_fwd");
+  return 0;
+}
+
+int mmt_readout_norm_bwd(const float* dv, const float* v, const float* inv_norm, int32_t B,
+                         int32_t S, int32_t M, int32_t T, int32_t d, float* dh, void* stream) {
+  MMT_ARG_CHECK(dv && v && inv_norm && dh, MMT_E_ARG, "mmt_readout_norm_bwd: null pointer");
+  MMT_ARG_CHECK(S == 1 + M * (T + 1), MMT_E_SHAPE, "mmt_readout_norm_bwd: S=%d != 1+M*(T+1)", S);
+  CHECK_D(d);
+  cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)B * S * d, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_status(e, "readout_bwd memset");
+  DISPATCH_VEC(d, (readout_bwd_kernel<V><<<(B * M + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(dv, v, inv_norm, B, S, M, T, dh)));
+  MMT_LAUNCH_CHECK("readout_bwd");
+  return 0;
+}
+
+int mmt_colsum(const float* X, int64_t rows, int32_t n, int64_t ld, int32_t rb, int64_t rbs,
+               float* out, int accumulate, void* stream) {
+  MMT_ARG_CHECK(X && out, MMT_E_ARG, "mmt_colsum: null pointer");
+  MMT_ARG_CHECK(n > 0 && rb >= 0, MMT_E_SHAPE, "mmt_colsum: n=%d rb=%d", n, rb);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_status(e, "colsum memset");
+  }
+  if (rows == 0) return 0;
+  const bool vec = (n % 4 == 0) && (ld % 4 == 0) && (rbs % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
+                   ((uintptr_t)out % 16 == 0);
+  int gx = ((n + 3) / 4 + 31) / 32;
+  int64_t want = (rows + 63) / 64;
+  int64_t cap = 4 * num_sms() / gx + 1;
+  int gy = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  if (vec) colsum_kernel<true><<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, rows, n, ld, rb, rbs, out);
+  else colsum_kernel<false><<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, rows, n, ld, rb, rbs, out);
+  MMT_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, uint64_t seed,
+                uint32_t site, void* stream) {
+  MMT_ARG_CHECK(in && out, MMT_E_ARG, "mmt_dropout: null pointer");
+  MMT_ARG_CHECK(n % 4 == 0, MMT_E_ALIGN, "mmt_dropout: n=%d must be a multiple of 4", n);
+  MMT_ARG_CHECK(p > 0.f && p < 1.f, MMT_E_ARG, "mmt_dropout: p=%f out of (0,1)", (double)p);
+  const int64_t total = rows * (n / 4);
+  if (total == 0) return 0;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  dropout_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n / 4, p, seed, site);
+  MMT_LAUNCH_CHECK("dropout");
+  return 0;
+}
+
+}  // extern "C"

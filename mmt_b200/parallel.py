@@ -1,0 +1,77 @@
+"""Data-parallel train step: one process per GPU, NCCL over NVLink/NVSwitch.
+
+The reference only has a (non-functional for >1 GPU) nn.DataParallel wrapper
+(base/base_trainer.py:49-50, trainer/trainer.py:182-199: gather embeddings, one global
+similarity + loss).  Here rank r owns samples [r*B/W, (r+1)*B/W); there are exactly two exchange
+steps per train step:
+
+  forward : ONE all-gather of the per-rank head inputs -- video expert embeddings [B/W, M, d] and
+            text features [B/W, text_dim] -- after which every rank evaluates the (tiny) text head,
+            similarity matrix and loss on the GLOBAL batch, so BatchNorm statistics and the loss
+            are exactly those of the single-device reference at batch B (no SyncBN collective);
+  backward: ONE all-reduce(SUM) of the flat gradient buffer.  Encoder gradients are per-rank
+            partial sums of the global-mean loss; head gradients are identical on every rank and
+            are pre-scaled by 1/W (exact for W a power of two) so the same SUM leaves them intact.
+"""
+import torch
+import torch.distributed as dist
+
+from . import engine
+
+
+def _all_gather_rows(x, group):
+  w = dist.get_world_size(group)
+  out = torch.empty((w * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+  dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+  return out
+
+
+def head_segments(layout):
+  """[(offset, numel)] contiguous runs of the flat buffer that belong to the text head."""
+  runs = []
+  for seg in layout.segments.values():
+    if not seg.head:
+      continue
+    if runs and runs[-1][0] + runs[-1][1] >= seg.offset:
+      runs[-1] = (runs[-1][0], seg.offset + seg.numel - runs[-1][0])
+    else:
+      runs.append((seg.offset, seg.numel))
+  return runs
+
+
+class DPEncodeFn(torch.autograd.Function):
+  """EncodeFn with the embedding all-gather inside (forward) and the gradient all-reduce
+  (backward).  Returns GLOBAL-batch (vid, txt, tw)."""
+
+  @staticmethod
+  def forward(ctx, anchor, text, net, feats, maxp, ft, ind, training, seed, group):
+    rank = dist.get_rank(group)
+    vid_l, sv_v = engine.video_forward(net.cfg, net.flat, feats, maxp, ft, ind, training,
+                                       seed + 7919 * (rank + 1))        # per-rank dropout masks
+    vid = _all_gather_rows(vid_l, group)
+    text_g = _all_gather_rows(text, group)
+    # identical seed on every rank: the head runs redundantly on the global batch
+    txt, tw, sv_h = engine.head_forward(net.cfg, net.flat, net.buf_flat, text_g, training, seed)
+    ctx.net, ctx.sv, ctx.group = net, (sv_v, sv_h), group
+    ctx.local_rows = (vid_l.shape[0], text.shape[0])
+    return vid, txt, tw
+
+  @staticmethod
+  def backward(ctx, dvid, dtxt, dtw):
+    net, (sv_v, sv_h), group = ctx.net, ctx.sv, ctx.group
+    w, rank = dist.get_world_size(group), dist.get_rank(group)
+    bl, rl = ctx.local_rows
+    accumulate = any(p.grad is not None for p in net._hot_params())
+    gflat = torch.empty_like(net.flat) if accumulate else net._grad_flat()
+    engine.zero_small_grads(net.cfg, gflat)
+    dtext_g = engine.head_backward(net.cfg, net.flat, gflat, sv_h, dtxt.contiguous(),
+                                   dtw.contiguous(), need_dtext=ctx.needs_input_grad[1])
+    engine.video_backward(net.cfg, net.flat, gflat, sv_v,
+                          dvid[rank * bl:(rank + 1) * bl].contiguous())
+    for off, n in head_segments(net.layout):
+      gflat[off:off + n].mul_(1.0 / w)
+    dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=group)
+    net._publish_grads(gflat, accumulate)
+    ctx.sv = None
+    dtext = dtext_g[rank * rl:(rank + 1) * rl] if dtext_g is not None else None
+    return None, dtext, None, None, None, None, None, None, None, None

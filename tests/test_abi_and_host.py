@@ -1,0 +1,232 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares with matching arity, and the host-side kernel sequencing (mmt_b200/engine.py) addresses
+only memory it owns (dry run against a recording stub of the library -- no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from mmt_b200 import _lib, engine
+from oracle import mmt_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+  src = open(os.path.join(ROOT, "include", "mmt_b200.h")).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  out = {}
+  for m in re.finditer(r"\b(?:int|int64_t)\s+(mmt_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    args = m.group(2).strip()
+    n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    out[m.group(1)] = n
+  return out
+
+
+def test_header_and_binding_agree():
+  fns = _header_functions()
+  assert len(fns) >= 20
+  assert set(fns) == set(_lib.SIGNATURES), set(fns) ^ set(_lib.SIGNATURES)
+  for name, n in fns.items():
+    assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_library_loads_and_exports_every_symbol():
+  if not os.path.isfile(_lib.LIB_PATH):
+    import __graft_entry__ as g
+    g.build()
+  lib = ctypes.CDLL(_lib.LIB_PATH)
+  for name in _header_functions():
+    assert hasattr(lib, name), name
+  lib.mmt_version.restype = ctypes.c_int32
+  assert lib.mmt_version() >= 100
+
+
+def test_gemm_desc_matches_header_struct():
+  src = open(os.path.join(ROOT, "include", "mmt_b200.h")).read()
+  body = re.search(r"typedef struct mmt_gemm_desc \{(.*?)\} mmt_gemm_desc;", src, flags=re.S).group(1)
+  body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+  names = []
+  for decl in body.split(";"):
+    decl = decl.strip()
+    if not decl:
+      continue
+    decl = re.sub(r"^(const\s+)?(float\*|int32_t|int64_t|float)\s*", "", decl)
+    names += [n.strip().lstrip("*") for n in decl.split(",")]
+  assert names == [f[0] for f in _lib.GemmDesc._fields_]
+
+
+class _Recorder:
+  """Stands in for libmmt_b200.so: checks that every pointer/extent a call receives lies inside a
+  tensor the host code allocated."""
+
+  def __init__(self):
+    self.ranges = []
+    self.calls = []
+
+  def note(self, t):
+    if t is not None:
+      st = t.untyped_storage()
+      self.ranges.append((st.data_ptr(), st.data_ptr() + st.nbytes()))
+
+  def inside(self, p, nbytes):
+    return any(lo <= p and p + nbytes <= hi for lo, hi in self.ranges)
+
+  def mmt_gemm(self, dref, stream):
+    d = dref._obj
+    self.calls.append("mmt_gemm")
+    M, N, K = d.M, d.N, d.K
+    for z in range(d.batch):
+      z0, z1 = z // d.batch_inner, z % d.batch_inner
+      a = d.A + 4 * (z0 * d.a_bs0 + z1 * d.a_bs1)
+      b = d.B + 4 * (z0 * d.b_bs0 + z1 * d.b_bs1)
+      c = d.C + 4 * (z0 * d.c_bs0 + z1 * d.c_bs1)
+
+      def a_off(m, k):
+        if d.a_kb > 0:
+          return m * d.a_ms + (k // d.a_kb) * d.a_kbs + (k % d.a_kb) * d.a_ks
+        return m * d.a_ms + k * d.a_ks
+
+      def c_off(m, n):
+        if d.c_mb > 0:
+          return (m // d.c_mb) * d.c_mbs + (m % d.c_mb) * d.c_ms + n
+        return m * d.c_ms + n
+
+      for (m, k) in ((0, 0), (M - 1, K - 1), (M - 1, 0), (0, K - 1)):
+        assert self.inside(a + 4 * a_off(m, k), 4), ("A", M, N, K, m, k)
+      for (n, k) in ((0, 0), (N - 1, K - 1)):
+        assert self.inside(b + 4 * (n * d.b_ns + k * d.b_ks), 4), ("B", M, N, K)
+      for (m, n) in ((0, 0), (M - 1, N - 1)):
+        assert self.inside(c + 4 * c_off(m, n), 4), ("C", M, N, K)
+        if d.aux:
+          assert self.inside(d.aux + 4 * (z0 * d.c_bs0 + z1 * d.c_bs1 + c_off(m, n)), 4)
+        if d.add:
+          assert self.inside(d.add + 4 * (z0 * d.c_bs0 + z1 * d.c_bs1 + c_off(m, n)), 4)
+      if d.bias:
+        assert self.inside(d.bias + 4 * (z * d.bias_bs + N - 1), 4)
+    return 0
+
+  def __getattr__(self, name):
+    if not name.startswith("mmt_"):
+      raise AttributeError(name)
+
+    def f(*args):
+      self.calls.append(name)
+      for a in args:
+        if isinstance(a, int) and a > (1 << 32):      # looks like a pointer
+          assert self.inside(a, 4), (name, hex(a))
+      return 0
+    return f
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+  rec = _Recorder()
+  real_ptr = _lib.ptr
+
+  def ptr(t, offset=0):
+    rec.note(t)
+    return real_ptr(t, offset)
+
+  monkeypatch.setattr(_lib, "_lib", rec)
+  monkeypatch.setattr(_lib, "ptr", ptr)
+  monkeypatch.setattr(engine, "ptr", ptr)
+  monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
+  monkeypatch.setattr(engine, "stream_ptr", lambda: 0)
+  return rec
+
+
+def _mini_net():
+  import types
+  from mmt_b200.model.model import CENet
+  ed = O.compute_dims(["s3d", "vggish", "ocr"])
+  vb = {"hidden_size": 128, "num_hidden_layers": 2, "num_attention_heads": 4,
+        "intermediate_size": 256, "hidden_act": "gelu", "hidden_dropout_prob": 0.1,
+        "attention_probs_dropout_prob": 0.1, "max_position_embeddings": 32, "type_vocab_size": 19,
+        "initializer_range": 0.02, "layer_norm_eps": 1e-12}
+
+  class Stub(torch.nn.Module):
+    def __init__(self):
+      super().__init__()
+      self.config = types.SimpleNamespace(hidden_size=96)
+
+  net = CENet(l2renorm=False, expert_dims=ed, tokenizer=None, keep_missing_modalities=True,
+              test_caption_mode="indep", txt_inp="bertftn", txt_agg="bertftn", txt_wgh="emb",
+              vid_wgh="none", vid_cont="bert", vid_inp="both", pos_enc="tint", out_tok="mxp",
+              same_dim=128, vid_bert_params=vb, txt_pro="gbn",
+              txt_bert_params={"hidden_dropout_prob": 0.1, "attention_probs_dropout_prob": 0.1},
+              txt_bert=Stub())
+  return net, ed
+
+
+def test_engine_dry_run_addresses_only_owned_memory(recorder):
+  net, ed = _mini_net()
+  B, T = 5, 7
+  batch = O.synth_batch(ed, B, T, text_dim=96)
+  mods = list(ed.keys())
+  feats = [batch["features"][m] for m in mods]
+  maxp = [batch["features_maxpool"][m] for m in mods]
+  ft = torch.stack([batch["features_t"][m] for m in mods], 0)
+  ind = torch.stack([batch["features_ind"][m] for m in mods], 0)
+  for training in (True, False):
+    vid, txt, tw, sv = engine.encode_forward(net.cfg, net.flat, net.buf_flat, batch["text_feat"],
+                                             feats, maxp, ft, ind, training, 123)
+    assert vid.shape == (B, 3, 128) and txt.shape == (B, 3, 128) and tw.shape == (B, 3)
+    g = torch.zeros_like(net.flat)
+    dtext = engine.encode_backward(net.cfg, net.flat, g, sv, torch.zeros_like(vid),
+                                   torch.zeros_like(txt), torch.zeros_like(tw))
+    assert dtext.shape == (B, 96)
+  sims, dots = engine.sims_forward(vid, txt, torch.ones(B, 3) / 3, tw, 1, True)
+  engine.sims_backward(torch.zeros_like(sims), dots, vid, txt, torch.ones(B, 3) / 3, tw, 1, True)
+  engine.max_margin(sims, 0.05, True)
+  assert recorder.calls.count("mmt_gemm") > 60
+  for name in ("mmt_embed_ln_fwd", "mmt_embed_ln_bwd", "mmt_res_ln_fwd", "mmt_res_ln_bwd",
+               "mmt_softmax_mask_fwd", "mmt_softmax_mask_bwd", "mmt_readout_norm_fwd",
+               "mmt_readout_norm_bwd", "mmt_geu_gate_fwd", "mmt_geu_gate_bwd", "mmt_dropout",
+               "mmt_moe_softmax_fwd", "mmt_moe_softmax_bwd", "mmt_sims_combine_fwd",
+               "mmt_sims_combine_bwd", "mmt_max_margin_fwd_bwd", "mmt_colsum"):
+    assert name in recorder.calls, name
+
+
+def test_cenet_keeps_reference_state_dict_names_and_flat_views():
+  net, ed = _mini_net()
+  P = O.init_params(ed, net.vid_bert_params, text_dim=96, same_dim=128)
+  sd = net.state_dict()
+  assert set(sd.keys()) == set(P.keys())
+  for k in P:
+    assert tuple(sd[k].shape) == tuple(P[k].shape), k
+  net.load_state_dict(P)
+  L = net.layout
+  # Q|K|V weights are one contiguous [3d, d] block of the flat buffer
+  q = L.off("vid_bert.encoder.layer.0.attention.self.query.weight")
+  qkv = net.flat[q:q + 3 * 128 * 128].view(3 * 128, 128)
+  assert torch.equal(qkv[128:256], P["vid_bert.encoder.layer.0.attention.self.key.weight"])
+  # parameters are views: an in-place optimiser update lands in the flat buffer
+  p = net._param("text_GU.ocr.fc.weight")
+  with torch.no_grad():
+    p.add_(1.0)
+  o = L.off("text_GU.ocr.fc.weight")
+  assert torch.equal(net.flat[o:o + p.numel()].view_as(p), p)
+  # text GEU fc weights of all experts form one [M*d, text_dim] matrix
+  o0 = L.off("text_GU.%s.fc.weight" % list(ed.keys())[0])
+  assert L.off("text_GU.%s.fc.weight" % list(ed.keys())[1]) == o0 + 128 * 96
+
+
+def test_unsupported_branches_raise():
+  from mmt_b200.model.model import CENet
+  ed = O.compute_dims(["s3d"])
+  with pytest.raises(NotImplementedError):
+    CENet(l2renorm=False, expert_dims=ed, tokenizer=None, keep_missing_modalities=True,
+          test_caption_mode="indep", txt_agg="bertftn", vid_cont="coll", vid_inp="both",
+          pos_enc="tint", out_tok="mxp", vid_wgh="none", txt_wgh="emb", txt_pro="gbn",
+          vid_bert_params={"hidden_size": 512})
+
+
+def test_product_path_fails_loudly_without_cuda():
+  net, ed = _mini_net()
+  batch = O.synth_batch(ed, 2, 3, text_dim=96)
+  with pytest.raises(RuntimeError, match="CUDA"):
+    net(batch["token_ids"], batch["features"], batch["features_t"], batch["features_ind"],
+        batch["features_avgpool"], batch["features_maxpool"], batch["query_masks"])

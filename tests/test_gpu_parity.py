@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs, plus the committed golden fixtures.  Tolerance: 1e-3 relative fp32 (BASELINE.json
+north_star); the fp32 CUDA-core mode is held to 2e-4."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmt_oracle as O
+import mmt_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+TOL_FP32 = 2e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+  assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+  from mmt_b200 import _lib
+  _lib.load()          # fails loudly if libmmt_b200.so is missing
+  return torch.device("cuda")
+
+
+# ------------------------------------------------------------------------------- GEMM
+def _ref_gemm(A, B, bias=None, add=None):
+  r = A.double() @ B.double().t()
+  if bias is not None:
+    r = r + bias.double()
+  if add is not None:
+    r = r + add.double()
+  return r
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 96, 300), (13, 7, 768), (512, 512, 1000),
+                                   (1, 1, 1), (300, 1536, 512)])
+def test_gemm_fp32_layouts(dev, M, N, K):
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(M * 7 + N)
+  A = torch.randn(M, K, generator=g).to(dev)
+  B = torch.randn(N, K, generator=g).to(dev)
+  bias = torch.randn(N, generator=g).to(dev)
+  add = torch.randn(M, N, generator=g).to(dev)
+  ref = _ref_gemm(A, B, bias, add)
+  for a_t in (False, True):
+    for b_t in (False, True):
+      Am = A.t().contiguous() if a_t else A          # a_t: stored [K, M]
+      Bm = B.t().contiguous() if b_t else B
+      C = torch.empty(M, N, device=dev)
+      _lib.gemm(M, N, K, Am, 1 if a_t else K, M if a_t else 1, Bm, 1 if b_t else K,
+                N if b_t else 1, C, N, bias=bias, add=add)
+      assert H.rel_err(C, ref) < 2e-5, (a_t, b_t)
+
+
+def test_gemm_epilogues_batch_remap_splitk(dev):
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(5)
+  M, N, K = 150, 260, 96
+  A = torch.randn(M, K, generator=g).to(dev)
+  B = torch.randn(N, K, generator=g).to(dev)
+  bias = torch.randn(N, generator=g).to(dev)
+  u_ref = _ref_gemm(A, B, bias)
+  f = torch.empty(M, N, device=dev)
+  u = torch.empty(M, N, device=dev)
+  _lib.gemm(M, N, K, A, K, 1, B, K, 1, f, N, bias=bias, epilogue=_lib.EPI_GELU, aux=u)
+  assert H.rel_err(u, u_ref) < 2e-5
+  assert H.rel_err(f, O.gelu(u_ref)) < 2e-5
+  # dgelu epilogue: C = (A B^T) * gelu'(aux)
+  dg = torch.empty(M, N, device=dev)
+  _lib.gemm(M, N, K, A, K, 1, B, K, 1, dg, N, epilogue=_lib.EPI_DGELU, aux=u)
+  ur = u_ref.clone().requires_grad_(True)
+  O.gelu(ur).sum().backward()
+  assert H.rel_err(dg, _ref_gemm(A, B) * ur.grad) < 2e-5
+  # batched, two-level batch index, strided heads (attention scores layout)
+  Bt, Hh, S, dh = 3, 4, 37, 128
+  qkv = torch.randn(Bt * S, 3 * Hh * dh, generator=g).to(dev)
+  Sp = (S + 3) // 4 * 4
+  P = torch.zeros(Bt, Hh, S, Sp, device=dev)
+  d = Hh * dh
+  _lib.gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=Bt * Hh, batch_inner=Hh,
+            a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(Hh * S * Sp, S * Sp))
+  q = qkv[:, :d].view(Bt, S, Hh, dh).permute(0, 2, 1, 3).double()
+  k = qkv[:, d:2 * d].view(Bt, S, Hh, dh).permute(0, 2, 1, 3).double()
+  assert H.rel_err(P[..., :S], q @ k.transpose(-1, -2)) < 2e-5
+  # output row remap (ReduceDim writes into token slots) and 2-level K index (its wgrad)
+  Bb, T, Sx, dd, din = 4, 5, 13, 128, 70
+  x = torch.randn(Bb * T, din, generator=g).to(dev)
+  W = torch.randn(dd, din, generator=g).to(dev)
+  proj = torch.zeros(Bb * Sx, dd, device=dev)
+  _lib.gemm(Bb * T, dd, din, x, din, 1, W, din, 1, proj, dd, c_off=2 * dd, c_mb=T, c_mbs=Sx * dd)
+  ref = _ref_gemm(x, W).view(Bb, T, dd)
+  assert H.rel_err(proj.view(Bb, Sx, dd)[:, 2:2 + T], ref) < 2e-5
+  assert float(proj.view(Bb, Sx, dd)[:, :2].abs().max()) == 0.0
+  dW = torch.empty(dd, din, device=dev)
+  _lib.gemm(dd, din, Bb * T, proj, 1, dd, x, 1, din, dW, din, a_off=2 * dd, a_kb=T, a_kbs=Sx * dd)
+  assert H.rel_err(dW, ref.reshape(Bb * T, dd).t() @ x.double()) < 2e-5
+  # split-K (weight-gradient shape)
+  Kl = 6000
+  dY = torch.randn(Kl, 256, generator=g).to(dev)
+  X = torch.randn(Kl, 384, generator=g).to(dev)
+  dW = torch.empty(256, 384, device=dev)
+  _lib.gemm(256, 384, Kl, dY, 1, 256, X, 1, 384, dW, 384)
+  assert H.rel_err(dW, dY.double().t() @ X.double()) < 2e-5
+
+
+def test_gemm_rejects_bad_arguments(dev):
+  from mmt_b200 import _lib
+  A = torch.zeros(4, 4, device=dev)
+  with pytest.raises(RuntimeError, match="aux"):
+    _lib.gemm(4, 4, 4, A, 4, 1, A, 4, 1, A, 4, epilogue=_lib.EPI_GELU)
+  with pytest.raises(RuntimeError, match="shape"):
+    _lib.gemm(4, 4, -1, A, 4, 1, A, 4, 1, A, 4)
+
+
+# ------------------------------------------------------------------------------- row kernels
+def test_res_ln_fwd_bwd_matches_torch(dev):
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  rows, d = 333, 512
+  g = torch.Generator().manual_seed(1)
+  t = torch.randn(rows, d, generator=g)
+  r = torch.randn(rows, d, generator=g)
+  gamma = 1 + 0.1 * torch.randn(d, generator=g)
+  beta = 0.1 * torch.randn(d, generator=g)
+  dy = torch.randn(rows, d, generator=g)
+  dy2 = torch.randn(rows, d, generator=g)
+  tr, rr, gr, br = (x.double().requires_grad_(True) for x in (t, r, gamma, beta))
+  y_ref = torch.nn.functional.layer_norm(tr + rr, (d,), gr, br, 1e-12)
+  y_ref.backward((dy + dy2).double())
+  td, rd = t.to(dev), r.to(dev)
+  y = torch.empty(rows, d, device=dev)
+  mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+  _lib.check(lib.mmt_res_ln_fwd(_lib.ptr(td), _lib.ptr(rd), _lib.ptr(gamma.to(dev)),
+                                _lib.ptr(beta.to(dev)), rows, d, 1e-12, 0.0, 0, 0, _lib.ptr(y),
+                                _lib.ptr(mean), _lib.ptr(rstd), _lib.stream_ptr()), "res_ln_fwd")
+  assert H.rel_err(y, y_ref) < 1e-5
+  assert H.rel_err(td, t.double() + r.double()) < 1e-6           # z written in place
+  dz = torch.empty(rows, d, device=dev)
+  dgam, dbet, dbias = (torch.zeros(d, device=dev) for _ in range(3))
+  _lib.check(lib.mmt_res_ln_bwd(_lib.ptr(dy.to(dev)), _lib.ptr(dy2.to(dev)), _lib.ptr(td),
+                                _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma.to(dev)), rows, d,
+                                0.0, 0, 0, _lib.ptr(dz), None, _lib.ptr(dgam), _lib.ptr(dbet),
+                                _lib.ptr(dbias), _lib.stream_ptr()), "res_ln_bwd")
+  assert H.rel_err(dz, tr.grad) < 2e-5
+  assert H.rel_err(dgam, gr.grad) < 2e-5
+  assert H.rel_err(dbet, br.grad) < 2e-5
+  assert H.rel_err(dbias, tr.grad.sum(0)) < 2e-5
+
+
+def test_softmax_mask_fwd_bwd(dev):
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  B, Hh, S = 3, 4, 45
+  Sp = 48
+  g = torch.Generator().manual_seed(2)
+  sc = torch.randn(B, Hh, S, Sp, generator=g)
+  mask = (torch.rand(B, S, generator=g) > 0.3).float()
+  mask[:, 0] = 1
+  scale = 1 / math.sqrt(128)
+  x = (sc[..., :S].double() * scale + (1 - mask.double())[:, None, None, :] * -10000.0).requires_grad_(True)
+  p_ref = torch.softmax(x, -1)
+  dP = torch.randn(B, Hh, S, Sp, generator=g)
+  p_ref.backward(dP[..., :S].double())
+  P = sc.to(dev)
+  _lib.check(lib.mmt_softmax_mask_fwd(_lib.ptr(P), _lib.ptr(mask.to(dev)), B, Hh, S, Sp, scale, 0.0,
+                                      0, 0, _lib.ptr(P), None, _lib.stream_ptr()), "softmax_fwd")
+  assert H.rel_err(P[..., :S], p_ref) < 1e-5
+  assert float(P[..., S:].abs().max()) == 0.0
+  dPd = dP.to(dev)
+  _lib.check(lib.mmt_softmax_mask_bwd(_lib.ptr(dPd), _lib.ptr(P), B, Hh, S, Sp, scale, 0.0, 0, 0,
+                                      _lib.stream_ptr()), "softmax_bwd")
+  assert H.rel_err(dPd[..., :S], x.grad * scale) < 2e-5     # gradient w.r.t. the raw QK^T
+
+
+def test_dropout_is_deterministic_unbiased_and_regenerated(dev):
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  rows, n, p = 4096, 512, 0.1
+  x = torch.ones(rows, n, device=dev)
+  o1, o2, o3 = (torch.empty_like(x) for _ in range(3))
+  st = _lib.stream_ptr()
+  _lib.check(lib.mmt_dropout(_lib.ptr(x), _lib.ptr(o1), rows, n, p, 11, 3, st), "dropout")
+  _lib.check(lib.mmt_dropout(_lib.ptr(x), _lib.ptr(o2), rows, n, p, 11, 3, st), "dropout")
+  _lib.check(lib.mmt_dropout(_lib.ptr(x), _lib.ptr(o3), rows, n, p, 12, 3, st), "dropout")
+  assert torch.equal(o1, o2)                                  # same (seed, site) -> same mask
+  assert not torch.equal(o1, o3)
+  keep = float((o1 > 0).float().mean())
+  assert abs(keep - (1 - p)) < 3e-3                            # keep-rate
+  assert abs(float(o1.mean()) - 1.0) < 5e-3                    # inverted-dropout scaling
+  vals = torch.unique(o1)
+  assert len(vals) == 2 and abs(float(vals.max()) - 1 / (1 - p)) < 1e-6
+
+
+# ------------------------------------------------------------------------------- head / loss
+def test_sims_and_loss_match_golden_and_ranking_is_exact(dev, golden_dir):
+  from mmt_b200.model.model import sharded_cross_view_inner_product
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  z = np.load(os.path.join(golden_dir, "sims_loss.npz"))
+  mods = ["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"]
+  vid = {m: torch.from_numpy(z["vid/" + m]).to(dev) for m in mods}
+  txt = {m: torch.from_numpy(z["txt/" + m]).to(dev) for m in mods}
+  vw, tw = torch.from_numpy(z["vw"]).to(dev), torch.from_numpy(z["tw"]).to(dev)
+  for merge in ("avg", "indep"):
+    s = sharded_cross_view_inner_product(vid, txt, vw, tw, mods, merge)
+    ref = z["sims_" + merge]
+    assert s.shape == ref.shape
+    np.testing.assert_allclose(s.cpu().numpy(), ref, rtol=0, atol=2e-6)
+    a = np.argsort(-s.cpu().numpy(), axis=1, kind="stable")
+    b = np.argsort(-ref, axis=1, kind="stable")
+    assert (a == b).all()                  # ranking indices bit-exact at the similarity boundary
+  # CPU inputs are accepted (eval path, trainer.py:396-403) and come back on the CPU
+  s_cpu = sharded_cross_view_inner_product({m: v.cpu() for m, v in vid.items()},
+                                           {m: v.cpu() for m, v in txt.items()}, vw.cpu(),
+                                           tw.cpu(), mods, "indep")
+  assert s_cpu.device.type == "cpu"
+  for margin, fix in ((0.05, True), (0.2, True), (0.05, False)):
+    x = torch.from_numpy(z["sims_avg"]).to(dev).requires_grad_(True)
+    l = MaxMarginRankingLoss(margin=margin, fix_norm=fix)(x)
+    np.testing.assert_allclose(float(l), float(z["loss_m%g_fix%d" % (margin, fix)]), rtol=2e-6)
+    l.backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), z["dloss_m%g_fix%d" % (margin, fix)],
+                               rtol=1e-5, atol=1e-9)
+  with pytest.raises(ValueError):
+    sharded_cross_view_inner_product(vid, txt, vw, tw, mods, "bogus")
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 1000, 2048])
+def test_max_margin_sizes(dev, n):
+  from mmt_b200 import engine
+  g = torch.Generator().manual_seed(n)
+  x = (torch.rand(n, n, generator=g) * 2 - 1)
+  xr = x.double().requires_grad_(True)
+  ref = O.max_margin_ranking_loss(xr, 0.05, True)
+  loss, dx = engine.max_margin(x.to(dev), 0.05, True)
+  if n == 1:
+    assert torch.isnan(loss)               # empty mean, like the reference (loss.py:63-65)
+    return
+  ref.backward()
+  assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+  assert H.rel_err(dx, xr.grad) < 1e-5
+
+
+def test_sims_backward_matches_oracle_autograd(dev):
+  from mmt_b200.model.model import SimsFn
+  g = torch.Generator().manual_seed(9)
+  Nv, caps, M, d = 10, 2, 5, 256
+  vid = torch.nn.functional.normalize(torch.randn(Nv, M, d, generator=g), dim=-1)
+  txt = torch.nn.functional.normalize(torch.randn(Nv * caps, M, d, generator=g), dim=-1)
+  vw = torch.nn.functional.normalize(torch.rand(Nv, M, generator=g), p=1, dim=-1)
+  tw = torch.softmax(torch.randn(Nv * caps, M, generator=g), -1)
+  w = torch.randn(Nv, Nv, generator=g)
+  vr, tr, twr = (x.double().requires_grad_(True) for x in (vid, txt, tw))
+  s_ref = O.sharded_cross_view_inner_product(
+      {m: vr[:, m] for m in range(M)}, {m: tr[:, m].view(Nv, caps, d) for m in range(M)},
+      vw.double(), twr.view(Nv, caps, M), list(range(M)), "avg")
+  (s_ref * w.double()).sum().backward()
+  vc, tc, twc = (x.to(dev).requires_grad_(True) for x in (vid, txt, tw))
+  s = SimsFn.apply(vc, tc, vw.to(dev), twc, caps, True)
+  (s * w.to(dev)).sum().backward()
+  assert H.rel_err(s, s_ref) < 1e-5
+  assert H.rel_err(vc.grad, vr.grad) < 2e-5
+  assert H.rel_err(tc.grad, tr.grad) < 2e-5
+  assert H.rel_err(twc.grad, twr.grad) < 2e-5
+
+
+def test_adam_matches_torch(dev):
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  n = 10007
+  g = torch.Generator().manual_seed(4)
+  p0 = torch.randn(n, generator=g)
+  pr = p0.clone().requires_grad_(True)
+  opt = torch.optim.Adam([pr], lr=5e-5, weight_decay=0.01)
+  p, m, v = p0.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+  for step in range(1, 4):
+    gr = torch.randn(n, generator=g)
+    pr.grad = gr.clone()
+    opt.step()
+    _lib.check(lib.mmt_adam_step(_lib.ptr(p), _lib.ptr(gr.to(dev)), _lib.ptr(m), _lib.ptr(v), n, 5e-5,
+                                 0.9, 0.999, 1e-8, 0.01, step, 1.0, _lib.stream_ptr()), "adam")
+  assert float((p.cpu() - pr.detach()).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------- end to end
+def _run_both(modalities, B, T, layers, caps=1, training=True, **kw):
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  ed, vb, P, batch, cfg = H.make_case(modalities, B, T, layers=layers, caps=caps, **kw)
+  # oracle (CPU, fp32, autograd backward)
+  Pr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+        for k, v in P.items()}
+  new_stats = {}
+  out_ref = O.cenet_forward(Pr, batch, cfg, training=training, out="conf", new_stats=new_stats,
+                            text_feat=batch["text_feat"], return_intermediates=True)
+  net = H.build_cuda_net(ed, vb, P, batch)
+  net.train(training)
+  out = net(**H.batch_kwargs(batch, "cuda"), out="conf", device=torch.device("cuda"))
+  return ed, P, Pr, batch, cfg, out_ref, new_stats, net, out
+
+
+@pytest.mark.parametrize("modalities,B,T,layers", [
+    (["s3d", "vggish"], 8, 14, 4),                                  # C1 (BASELINE configs[0])
+    (["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"], 6, 30, 2),   # C2 geometry, small B
+])
+def test_train_step_parity_with_oracle(dev, modalities, B, T, layers):
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  ed, P, Pr, batch, cfg, out_ref, new_stats, net, out = _run_both(modalities, B, T, layers)
+  conf_ref = out_ref["cross_view_conf_matrix"]
+  conf = out["cross_view_conf_matrix"]
+  assert out["modalities"] == list(ed.keys())
+  assert H.rel_err(conf, conf_ref) < TOL_FP32 and H.rel_l2(conf, conf_ref) < TOL_FP32
+  loss_ref = O.max_margin_ranking_loss(conf_ref, 0.05, True)
+  loss = MaxMarginRankingLoss(margin=0.05, fix_norm=True)(conf)
+  assert abs(float(loss) - float(loss_ref)) < TOL_FP32 * abs(float(loss_ref))
+  loss_ref.backward()
+  loss.backward()
+  gmax = max(float(p.grad.abs().max()) for p in Pr.values() if getattr(p, "grad", None) is not None)
+  checked = 0
+  for name, pr in Pr.items():
+    if not (pr.is_floating_point() and pr.requires_grad):
+      continue
+    p = net._param(name)
+    if pr.grad is None:
+      assert p.grad is None, name                      # pooler: no gradient on either side
+      continue
+    assert p.grad is not None, name
+    scale = max(float(pr.grad.abs().max()), 1e-3 * gmax)
+    err = float((p.grad.cpu().double() - pr.grad.double()).abs().max()) / scale
+    assert err < TOL_FP32, (name, err)
+    checked += 1
+  assert checked >= 20 + 16 * layers
+  # BatchNorm running statistics (model.py:745-750 -> torch BatchNorm1d update)
+  for name, v in new_stats.items():
+    mod, leaf = net._leaf(name)
+    assert H.rel_err(mod._buffers[leaf], v) < 1e-5, name
+  assert int(net.nbt_flat[0]) == 1
+
+
+def test_eval_embds_two_captions(dev):
+  ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish", "ocr"], 5, 9, layers=2, caps=2)
+  ref = O.cenet_forward(P, batch, cfg, training=False, out="embds", text_feat=batch["text_feat"])
+  refc = O.cenet_forward(P, batch, cfg, training=False, out="conf", text_feat=batch["text_feat"])
+  net = H.build_cuda_net(ed, vb, P, batch).eval()
+  with torch.no_grad():
+    e = net(**H.batch_kwargs(batch, "cuda"), out="embds")
+    c = net(**H.batch_kwargs(batch, "cuda"), out="conf")
+  for k in ("vid_embds", "text_embds", "vid_weights", "text_weights"):
+    assert tuple(e[k].shape) == tuple(ref[k].shape), k
+    assert H.rel_err(e[k], ref[k]) < TOL_FP32, k
+  assert tuple(c["cross_view_conf_matrix"].shape) == (10, 5)
+  assert H.rel_err(c["cross_view_conf_matrix"], refc["cross_view_conf_matrix"]) < TOL_FP32
+  # t2v ranks equal the oracle's (model/metric.py semantics)
+  r1 = O.retrieval_ranks(c["cross_view_conf_matrix"].cpu().numpy())
+  r2 = O.retrieval_ranks(refc["cross_view_conf_matrix"].numpy())
+  assert (r1 == r2).all()
+
+
+def test_missing_experts_and_ragged_inputs(dev):
+  """All-padding experts (k=0 valid frames), position clamp, B not a multiple of anything."""
+  ed, vb, P, batch, cfg = H.make_case(["ocr", "speech", "s3d"], 7, 11, layers=1, seed=77)
+  batch["features_ind"]["ocr"][:] = 0            # expert entirely missing for every video
+  batch["features"]["ocr"][:] = 0
+  batch["features_maxpool"]["ocr"][:] = 0
+  batch["features_t"]["ocr"][:] = 1
+  batch["features_t"]["s3d"][0, 0] = 500.0       # clamp to max_pos - 1 (model.py:516)
+  ref = O.cenet_forward(P, batch, cfg, training=True, out="conf", text_feat=batch["text_feat"])
+  net = H.build_cuda_net(ed, vb, P, batch).train()
+  out = net(**H.batch_kwargs(batch, "cuda"))
+  assert H.rel_err(out["cross_view_conf_matrix"], ref["cross_view_conf_matrix"]) < TOL_FP32
+  assert torch.isfinite(out["cross_view_conf_matrix"]).all()
+
+
+def test_dropout_training_is_finite_and_close_in_expectation(dev):
+  ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish"], 8, 14, layers=2, dropout=0.1)
+  net = H.build_cuda_net(ed, vb, P, batch, dropout=0.1).train()
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  crit = MaxMarginRankingLoss(0.05, True)
+  outs = []
+  for _ in range(3):
+    net.zero_grad()
+    out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]
+    crit(out).backward()
+    assert torch.isfinite(out).all()
+    assert all(torch.isfinite(p.grad).all() for p in net._hot_params() if p.grad is not None)
+    outs.append(out.detach())
+  assert not torch.equal(outs[0], outs[1])       # a fresh mask every step
+  net.eval()
+  with torch.no_grad():
+    e1 = net(**H.batch_kwargs(batch, "cuda"), out="embds")["vid_embds"]
+    e2 = net(**H.batch_kwargs(batch, "cuda"), out="embds")["vid_embds"]
+  assert torch.equal(e1, e2)                     # eval: no dropout, deterministic
+
+
+def test_gradient_accumulation_and_optimizer_view_semantics(dev):
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish"], 4, 6, layers=1)
+  net = H.build_cuda_net(ed, vb, P, batch).train()
+  crit = MaxMarginRankingLoss(0.05, True)
+  crit(net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]).backward()
+  g1 = {n: net._param(n).grad.clone() for n in net._names if net._param(n).grad is not None}
+  crit(net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]).backward()   # no zero_grad
+  for n, g in g1.items():
+    assert H.rel_err(net._param(n).grad, 2 * g) < 1e-4, n
+  opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-3)
+  before = net.flat.clone()
+  opt.step()
+  assert not torch.equal(before, net.flat)       # the optimiser wrote through the views
