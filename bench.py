@@ -387,9 +387,44 @@ def cpu_step_fn(w, B, seed=1234):
   return step
 
 
+def usable_cpus():
+  """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota."""
+  try:
+    n = len(os.sched_getaffinity(0))
+  except AttributeError:
+    n = os.cpu_count() or 1
+  try:
+    q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+    if q != "max":
+      n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+  except Exception:
+    pass
+  return n
+
+
+def pick_threads(w):
+  """The reference does not set a thread count (torch default = all CPUs it sees).  To give the
+  CPU arm its best case, probe a few intra-op thread counts on a tiny step of the same model and
+  keep the fastest."""
+  n = usable_cpus()
+  cands = sorted(set([c for c in (4, 8, 16, 32, 64) if c <= n] + [n]))
+  small = dict(w, B=4)
+  best, best_t = cands[0], None
+  for c in cands:
+    torch.set_num_threads(c)
+    fn = cpu_step_fn(small, 4)
+    fn()
+    t0 = time.time()
+    fn()
+    dt = time.time() - t0
+    if best_t is None or dt < best_t:
+      best, best_t = c, dt
+  torch.set_num_threads(best)
+  return best
+
+
 def cpu_baseline(w, steps, warmup, budget_s):
-  cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
+  cores = pick_threads(w)
   B = w["B"]
   fn = cpu_step_fn(w, B)
   t0 = time.time()
@@ -415,8 +450,7 @@ def run_reference(args):
   if rank != 0:
     return
   w = WORKLOADS[args.workload]
-  cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
+  cores = pick_threads(w)
   B = w["B"]
   total = args.steps + args.warmup
   fn = cpu_step_fn(w, B)

@@ -52,12 +52,13 @@ int64_t mmt_launch_count(void);
  *   C(m,n) = C[(m / c_mb)*c_mbs + (m % c_mb)*c_ms + n]           (c_mb == 0: C[m*c_ms + n])
  * `add` and `aux` use C's addressing.  Batched: z in [0,batch): z0 = z / batch_inner,
  * z1 = z % batch_inner, operand X is offset by z0*x_bs0 + z1*x_bs1.
- * Weight-gradient shaped problems (few output tiles, long K, dense un-batched C) are split along
- * K across CTAs and reduced with fp32 atomics into a zeroed C.
+ * With MMT_GEMM_SPLIT_K set, weight-gradient shaped problems (few output tiles, long K, dense
+ * un-batched C) are split along K across CTAs and reduced with fp32 atomics into a zeroed C.
  * ------------------------------------------------------------------------------------------- */
 enum { MMT_EPI_NONE = 0,
        MMT_EPI_GELU = 1,    /* aux <- pre-activation u, C <- gelu_erf(u)        (bert.py:218-219,53) */
        MMT_EPI_DGELU = 2 }; /* C <- value * gelu_erf'(aux)   (autograd of bert.py:53)               */
+enum { MMT_GEMM_SPLIT_K = 1 };
 enum { MMT_PREC_FP32 = 0,   /* CUDA-core FMA, fp32 operands and accumulation (exact-order class)     */
        MMT_PREC_TF32 = 1 }; /* tcgen05 kind::tf32 tensor-core tiles, TMA-fed, fp32 accumulate in TMEM */
 
@@ -75,6 +76,9 @@ typedef struct mmt_gemm_desc {
   int64_t a_bs0, a_bs1, b_bs0, b_bs1, c_bs0, c_bs1;
   int64_t bias_bs;      /* bias of batch z starts at bias + z*bias_bs */
   int32_t precision;
+  int32_t flags;        /* MMT_GEMM_SPLIT_K: allow a split-K schedule (fp32 atomics, run-to-run
+                           summation order not fixed); forward GEMMs leave it clear so that the
+                           forward pass is bit-reproducible */
 } mmt_gemm_desc;
 
 int mmt_gemm(const mmt_gemm_desc* d, void* stream);

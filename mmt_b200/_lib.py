@@ -20,6 +20,7 @@ c_p = ctypes.c_void_p
 
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
 PREC_FP32, PREC_TF32 = 0, 1
+GEMM_SPLIT_K = 1
 
 
 class GemmDesc(ctypes.Structure):
@@ -35,6 +36,7 @@ class GemmDesc(ctypes.Structure):
       ("c_bs0", c_i64), ("c_bs1", c_i64),
       ("bias_bs", c_i64),
       ("precision", c_i32),
+      ("flags", c_i32),
   ]
 
 
@@ -120,7 +122,7 @@ def launch_count():
 def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_off=0, bias=None,
          bias_off=0, add=None, add_off=0, aux=None, aux_off=0, epilogue=EPI_NONE, alpha=1.0,
          a_kb=0, a_kbs=0, c_mb=0, c_mbs=0, batch=1, batch_inner=1, a_bs=(0, 0), b_bs=(0, 0),
-         c_bs=(0, 0), bias_bs=0, precision=PREC_FP32):
+         c_bs=(0, 0), bias_bs=0, precision=PREC_FP32, split_k=False):
   d = GemmDesc()
   d.M, d.N, d.K = M, N, K
   d.A, d.a_ms, d.a_ks, d.a_kb, d.a_kbs = ptr(A, a_off), a_ms, a_ks, a_kb, a_kbs
@@ -136,4 +138,5 @@ def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_
   d.c_bs0, d.c_bs1 = c_bs
   d.bias_bs = bias_bs
   d.precision = precision
+  d.flags = GEMM_SPLIT_K if split_k else 0
   check(load().mmt_gemm(ctypes.byref(d), stream_ptr()), "mmt_gemm")

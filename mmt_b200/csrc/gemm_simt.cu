@@ -154,7 +154,7 @@ int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
   GemmArgs args{d, 1, ((d.K + BK - 1) / BK) * BK};
   const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
   // weight-gradient shape: few output tiles, long K, dense un-batched C that is not also `add`
-  if (d.batch == 1 && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
+  if ((d.flags & MMT_GEMM_SPLIT_K) && d.batch == 1 && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
       d.add != d.C && tiles * 2 <= num_sms() && d.K >= 32 * BK) {
     int split = (2 * num_sms() + tiles - 1) / tiles;
     const int max_split = d.K / (8 * BK);

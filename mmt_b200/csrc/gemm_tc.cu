@@ -1,8 +1,379 @@
-// placeholder until the tcgen05 kernel lands (replaced below in this round)
+// tcgen05 TF32 GEMM for sm_100a (MMT_PREC_TF32): C = epilogue(alpha * A B^T + bias + add).
+//
+// Blackwell-native structure (no mma.sync / wgmma):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor tiles of A and B (fp32 in HBM, read as tf32)
+//              into a 3-stage 128B-swizzled shared-memory ring, mbarrier complete_tx signalling
+//   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma.cta_group::1.kind::tf32
+//              (M=128, N=BN, K=8 per instruction) with the fp32 accumulator in TMEM;
+//              tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-5: epilogue      -- tcgen05.ld the accumulator (one TMEM lane = one output row per
+//              thread), fuse bias / residual-add / erf-GELU (+ pre-activation side output) /
+//              GELU-derivative multiply, 128-bit global stores (or red.add for split-K)
+// Two CTAs are resident per SM (96 KB smem, 128 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+//
+// Operand layouts: both A and B may be K-major (contiguous along k) or MN-major (contiguous
+// along m / n); the latter is what the backward GEMMs (dgrad: B = W read "transposed"; wgrad:
+// A = dY^T, B = X^T) need, so no transposes are ever materialised.  The UMMA shared-memory
+// descriptors and the TMA boxes are built per layout (canonical SWIZZLE_128B atoms).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace mmt {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // 32 fp32 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 8;              // tf32: 32 B of K per instruction
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;   // bounded mbarrier spin: a protocol bug traps, never hangs
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+  return d;
+}
+
+struct TcArgs {
+  mmt_gemm_desc d;
+  int split_k;
+  int kb_per_split;    // k-blocks (of BK) per split
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b,
+                                                              const TcArgs args) {
+  constexpr uint32_t A_BYTES = BM * BK * 4;     // 16 KB
+  constexpr uint32_t B_BYTES = BN * BK * 4;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is only 16 B aligned by contract
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const mmt_gemm_desc& d = args.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ksplit = blockIdx.z;
+  const int num_kb_total = (d.K + BK - 1) / BK;
+  const int kb_begin = ksplit * args.kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + args.kb_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);                   // box {32 k, 128 m}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j)                                 // 4 boxes {32 m, 32 k}
+            tma_load_2d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, M=128, N=BN
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); k-step = +32 B inside the row
+      // MN-major : 32-element (128 B) chunks of m/n, chunks BK*128 B apart (LBO); k-step = one
+      //            8-row group = +1024 B
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
+      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * A_STEP, A_LBO, A_SBO);
+          const uint64_t db = make_smem_desc(sb + k * B_STEP, B_LBO, B_SBO);
+          umma_tf32(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);          // smem stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);            // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = (m < d.M) && (num_kb > 0);
+    int64_t row = 0;
+    if (row_ok) row = d.c_mb > 0 ? (int64_t)(m / d.c_mb) * d.c_mbs + (int64_t)(m % d.c_mb) * d.c_ms
+                                 : (int64_t)m * d.c_ms;
+    const bool lead = (ksplit == 0);
+    const bool vec_ok = ((d.c_ms & 3) == 0) && ((d.c_mbs & 3) == 0) && ((d.N & 3) == 0) &&
+                        ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);   // warp-collective
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= d.N) continue;
+      float* crow = d.C + row + nb;
+      const float* addrow = d.add ? d.add + row + nb : nullptr;
+      float* auxrow = d.aux ? d.aux + row + nb : nullptr;
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (nb + j >= d.N) break;
+          float4 o = make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha);
+          if (lead || args.split_k == 1) {
+            if (d.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(d.bias + nb + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (addrow) {
+              const float4 a = *reinterpret_cast<const float4*>(addrow + j);
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+          }
+          if (args.split_k > 1) {
+            atomicAdd(reinterpret_cast<float4*>(crow + j), o);
+            continue;
+          }
+          if (d.epilogue == MMT_EPI_GELU) {
+            *reinterpret_cast<float4*>(auxrow + j) = o;
+            o = make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w));
+          } else if (d.epilogue == MMT_EPI_DGELU) {
+            const float4 u = *reinterpret_cast<const float4*>(auxrow + j);
+            o.x *= dgelu_erf(u.x); o.y *= dgelu_erf(u.y); o.z *= dgelu_erf(u.z); o.w *= dgelu_erf(u.w);
+          }
+          *reinterpret_cast<float4*>(crow + j) = o;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j) {
+          if (nb + j >= d.N) break;
+          float o = v[j] * d.alpha;
+          if (lead || args.split_k == 1) {
+            if (d.bias) o += d.bias[nb + j];
+            if (addrow) o += addrow[j];
+          }
+          if (args.split_k > 1) { atomicAdd(crow + j, o); continue; }
+          if (d.epilogue == MMT_EPI_GELU) { auxrow[j] = o; o = gelu_erf(o); }
+          else if (d.epilogue == MMT_EPI_DGELU) o *= dgelu_erf(auxrow[j]);
+          crow[j] = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// rows x K operand, element (r, k) at base[r*rs + k*ks] with either ks == 1 (K-major) or rs == 1.
+int make_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
+             int tile_rows, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled unavailable");
+  const int64_t ld = mn_major ? ks : rs;
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0 && ld >= 1, MMT_E_ALIGN,
+                "gemm_tc: operand %s needs a 16-byte aligned base and stride (ld=%lld)", what, (long long)ld);
+  cuuint64_t dims[2], strides[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (!mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)tile_rows; }
+  else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; }
+  strides[0] = (cuuint64_t)ld * 4;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 /*align slack*/ + 128 /*barriers*/;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
+    configured = true;
+  }
+  dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
+  MMT_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+}  // namespace
+
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
-  set_error("mmt_gemm: MMT_PREC_TF32 not built");
-  return MMT_E_UNSUPPORTED;
+  MMT_ARG_CHECK(d.batch == 1, MMT_E_UNSUPPORTED, "gemm_tc: batched problems use MMT_PREC_FP32");
+  MMT_ARG_CHECK(d.a_kb == 0, MMT_E_UNSUPPORTED, "gemm_tc: two-level K index uses MMT_PREC_FP32");
+  const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
+  MMT_ARG_CHECK(!a_mn || d.a_ms == 1, MMT_E_UNSUPPORTED, "gemm_tc: A must be contiguous along k or m");
+  MMT_ARG_CHECK(!b_mn || d.b_ns == 1, MMT_E_UNSUPPORTED, "gemm_tc: B must be contiguous along k or n");
+  MMT_ARG_CHECK(d.K >= 1, MMT_E_SHAPE, "gemm_tc: K=%d", d.K);
+  constexpr int BN = 128;
+  TcArgs args{d, 1, (d.K + BK - 1) / BK};
+  const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
+  const int num_kb = (d.K + BK - 1) / BK;
+  if ((d.flags & MMT_GEMM_SPLIT_K) && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
+      d.add != d.C && tiles * 2 <= num_sms() && num_kb >= 32) {
+    int split = (2 * num_sms() + tiles - 1) / tiles;
+    if (split > num_kb / 8) split = num_kb / 8;
+    if (split > 1) {
+      args.kb_per_split = (num_kb + split - 1) / split;
+      args.split_k = (num_kb + args.kb_per_split - 1) / args.kb_per_split;
+      cudaError_t e = cudaMemsetAsync(d.C, 0, sizeof(float) * (size_t)d.M * d.N, stream);
+      if (e != cudaSuccess) return cuda_status(e, "gemm_tc split-K memset");
+    }
+  }
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, "A");
+  if (rc) return rc;
+  rc = make_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, "B");
+  if (rc) return rc;
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, args, stream);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, args, stream);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, args, stream);
+  return launch<BN, true, true>(ma, mb, args, stream);
 }
-}
+
+}  // namespace mmt

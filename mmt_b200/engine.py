@@ -242,7 +242,7 @@ def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
     dlog = _empty((R, M), flat)
     check(lib.mmt_moe_softmax_bwd(ptr(dtw), ptr(sv.tw), R, M, ptr(dlog), st), "mmt_moe_softmax_bwd")
     # dW_moe [M, td] = dlog^T @ tdrop ; db = colsum(dlog)
-    gemm(M, td, R, dlog, 1, M, sv.tdrop, 1, td, gflat, td, c_off=L.off("moe_fc_txt.%s.weight" % m0))
+    gemm(M, td, R, dlog, 1, M, sv.tdrop, 1, td, gflat, td, c_off=L.off("moe_fc_txt.%s.weight" % m0), split_k=True)
     colsum(dlog, R, M, M, L.off("moe_fc_txt.%s.bias" % m0))
     if need_dtext:
       dtext = _empty((R, td), flat)
@@ -262,12 +262,12 @@ def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
         ptr(gflat, L.off("text_GU.%s.cg.batch_norm.bias" % m0)), st), "mmt_geu_gate_bwd")
     # cg.fc: dW2_m [d,d] = dG_m^T @ X_m ; db2 = colsum(dG) ; dX += dG_m @ W2_m
     gemm(d, d, R, dG, 1, M * d, sv.X, 1, M * d, gflat, d, c_off=L.off("text_GU.%s.cg.fc.weight" % m0),
-         batch=M, a_bs=(d, 0), b_bs=(d, 0), c_bs=(d * d, 0))
+         batch=M, a_bs=(d, 0), b_bs=(d, 0), c_bs=(d * d, 0), split_k=True)
     colsum(dG, R, M * d, M * d, L.off("text_GU.%s.cg.fc.bias" % m0))
     gemm(R, d, d, dG, M * d, 1, flat, 1, d, dX, M * d, b_off=L.off("text_GU.%s.cg.fc.weight" % m0),
          add=dX, batch=M, a_bs=(d, 0), b_bs=(d * d, 0), c_bs=(d, 0))
     # fc: dW1 [M*d, td] = dX^T @ text ; db1 = colsum(dX) ; dtext += dX @ W1
-    gemm(M * d, td, R, dX, 1, M * d, sv.text, 1, td, gflat, td, c_off=L.off("text_GU.%s.fc.weight" % m0))
+    gemm(M * d, td, R, dX, 1, M * d, sv.text, 1, td, gflat, td, c_off=L.off("text_GU.%s.fc.weight" % m0), split_k=True)
     colsum(dX, R, M * d, M * d, L.off("text_GU.%s.fc.bias" % m0))
     if need_dtext:
       if dtext is None:
@@ -314,13 +314,13 @@ def video_backward(cfg, flat, gflat, sv, dvid):
                              ptr(gflat, L.off(p + "output.dense.bias")), st), "mmt_res_ln_bwd")
     # FFN down: dW2 [d, ff] = dt2^T @ f ; du = (dt2 @ W2) * gelu'(u)
     gemm(d, ff, BS, dt2, 1, d, ls.f, 1, ff, gflat, ff, c_off=L.off(p + "output.dense.weight"),
-         precision=prec)
+         precision=prec, split_k=True)
     du = _empty((BS, ff), flat)
     gemm(BS, ff, d, dt2, d, 1, flat, 1, ff, du, ff, b_off=L.off(p + "output.dense.weight"),
          epilogue=EPI_DGELU, aux=ls.u, precision=prec)
     # FFN up: dW1 [ff, d] = du^T @ a ; db1 = colsum(du) ; da = du @ W1
     gemm(ff, d, BS, du, 1, ff, ls.a, 1, d, gflat, d, c_off=L.off(p + "intermediate.dense.weight"),
-         precision=prec)
+         precision=prec, split_k=True)
     colsum(du, BS, ff, ff, L.off(p + "intermediate.dense.bias"))
     da = _empty((BS, d), flat)
     gemm(BS, d, ff, du, ff, 1, flat, 1, d, da, d, b_off=L.off(p + "intermediate.dense.weight"),
@@ -336,7 +336,7 @@ def video_backward(cfg, flat, gflat, sv, dvid):
                              ptr(gflat, L.off(p + "attention.output.dense.bias")), st), "mmt_res_ln_bwd")
     # attention output dense: dWo = dt1^T @ ctx ; dctx = dt1 @ Wo
     gemm(d, d, BS, dt1, 1, d, ls.ctx, 1, d, gflat, d, c_off=L.off(p + "attention.output.dense.weight"),
-         precision=prec)
+         precision=prec, split_k=True)
     dctx = _empty((BS, d), flat)
     gemm(BS, d, d, dt1, d, 1, flat, 1, d, dctx, d, b_off=L.off(p + "attention.output.dense.weight"),
          precision=prec)
@@ -360,7 +360,7 @@ def video_backward(cfg, flat, gflat, sv, dvid):
          a_bs=bsP, b_bs=bsQ, c_bs=bsQ)
     # QKV projection: dWqkv [3d, d] = dqkv^T @ h_in ; dbqkv ; dh = dz1 + dqkv @ Wqkv
     gemm(3 * d, d, BS, dqkv, 1, 3 * d, ls.h_in, 1, d, gflat, d,
-         c_off=L.off(p + "attention.self.query.weight"), precision=prec)
+         c_off=L.off(p + "attention.self.query.weight"), precision=prec, split_k=True)
     colsum(dqkv, BS, 3 * d, 3 * d, L.off(p + "attention.self.query.bias"))
     dh_ = _empty((BS, d), flat)
     gemm(BS, d, 3 * d, dqkv, 3 * d, 1, flat, 1, d, dh_, d,
@@ -385,7 +385,7 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     base = (1 + k * (T + 1)) * d
     # dW [d, in] = dproj[AGG rows]^T @ maxpool  +  dproj[temporal rows]^T @ features
     gemm(d, din, B, dproj, 1, 0, sv.maxp[k], 1, din, gflat, din, a_off=base, a_kb=1, a_kbs=S * d,
-         c_off=w_off)
+         c_off=w_off, split_k=True)
     gemm(d, din, B * T, dproj, 1, d, sv.feats[k], 1, din, gflat, din, a_off=base + d, a_kb=T,
          a_kbs=S * d, c_off=w_off, add=gflat, add_off=w_off)
     colsum(dproj, B * (T + 1), d, d, b_off, rb=T + 1, rbs=S * d, x_off=base)

@@ -102,7 +102,7 @@ def test_gemm_epilogues_batch_remap_splitk(dev):
   dY = torch.randn(Kl, 256, generator=g).to(dev)
   X = torch.randn(Kl, 384, generator=g).to(dev)
   dW = torch.empty(256, 384, device=dev)
-  _lib.gemm(256, 384, Kl, dY, 1, 256, X, 1, 384, dW, 384)
+  _lib.gemm(256, 384, Kl, dY, 1, 256, X, 1, 384, dW, 384, split_k=True)
   assert H.rel_err(dW, dY.double().t() @ X.double()) < 2e-5
 
 
@@ -136,18 +136,18 @@ def test_res_ln_fwd_bwd_matches_torch(dev):
   _lib.check(lib.mmt_res_ln_fwd(_lib.ptr(td), _lib.ptr(rd), _lib.ptr(gamma.to(dev)),
                                 _lib.ptr(beta.to(dev)), rows, d, 1e-12, 0.0, 0, 0, _lib.ptr(y),
                                 _lib.ptr(mean), _lib.ptr(rstd), _lib.stream_ptr()), "res_ln_fwd")
-  assert H.rel_err(y, y_ref) < 1e-5
-  assert H.rel_err(td, t.double() + r.double()) < 1e-6           # z written in place
+  e_y, e_z = H.rel_err(y, y_ref), H.rel_err(td, t.double() + r.double())
+  assert e_y < 1e-5, e_y
+  assert e_z < 1e-6, e_z                                         # z written in place
   dz = torch.empty(rows, d, device=dev)
   dgam, dbet, dbias = (torch.zeros(d, device=dev) for _ in range(3))
   _lib.check(lib.mmt_res_ln_bwd(_lib.ptr(dy.to(dev)), _lib.ptr(dy2.to(dev)), _lib.ptr(td),
                                 _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma.to(dev)), rows, d,
                                 0.0, 0, 0, _lib.ptr(dz), None, _lib.ptr(dgam), _lib.ptr(dbet),
                                 _lib.ptr(dbias), _lib.stream_ptr()), "res_ln_bwd")
-  assert H.rel_err(dz, tr.grad) < 2e-5
-  assert H.rel_err(dgam, gr.grad) < 2e-5
-  assert H.rel_err(dbet, br.grad) < 2e-5
-  assert H.rel_err(dbias, tr.grad.sum(0)) < 2e-5
+  errs = [H.rel_err(dz, tr.grad), H.rel_err(dgam, gr.grad), H.rel_err(dbet, br.grad),
+          H.rel_err(dbias, tr.grad.sum(0))]
+  assert max(errs) < 2e-5, errs
 
 
 def test_softmax_mask_fwd_bwd(dev):
@@ -400,10 +400,126 @@ def test_gradient_accumulation_and_optimizer_view_semantics(dev):
   crit = MaxMarginRankingLoss(0.05, True)
   crit(net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]).backward()
   g1 = {n: net._param(n).grad.clone() for n in net._names if net._param(n).grad is not None}
+  gmax = max(float(g.abs().max()) for g in g1.values())
   crit(net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]).backward()   # no zero_grad
   for n, g in g1.items():
-    assert H.rel_err(net._param(n).grad, 2 * g) < 1e-4, n
+    # key.bias gradients are analytically zero (rounding noise): floor the scale
+    err = float((net._param(n).grad - 2 * g).abs().max()) / max(float(g.abs().max()), 1e-3 * gmax)
+    assert err < 1e-4, (n, err)
   opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-3)
   before = net.flat.clone()
   opt.step()
   assert not torch.equal(before, net.flat)       # the optimiser wrote through the views
+
+
+# ------------------------------------------------------------------------------- tcgen05 TF32 path
+def _tf32_trunc(x):
+  return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep 10 mantissa bits
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 512), (200, 100, 300),
+                                   (13952, 512, 512), (1000, 3072, 512)])
+def test_gemm_tf32_all_operand_layouts(dev, M, N, K):
+  """tcgen05 kind::tf32 tiles, TMA-fed, for K-major and MN-major A / B (forward, dgrad, wgrad
+  layouts).  Checked against fp64 on tf32-truncated operands (tight) and on the raw operands
+  (tf32 error bound)."""
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(M + N + K)
+  Mp, Np, Kp = (M + 3) // 4 * 4, (N + 3) // 4 * 4, (K + 3) // 4 * 4      # 16-byte aligned strides
+  A = torch.randn(M, K, generator=g).to(dev)
+  B = torch.randn(N, K, generator=g).to(dev)
+  bias = torch.randn(N, generator=g).to(dev)
+  ref = _ref_gemm(A, B, bias)
+  ref_t = _ref_gemm(_tf32_trunc(A), _tf32_trunc(B), bias)
+  for a_mn in (False, True):
+    for b_mn in (False, True):
+      if a_mn:
+        Am = torch.zeros(K, Mp, device=dev); Am[:, :M] = A.t(); a_ms, a_ks = 1, Mp
+      else:
+        Am = torch.zeros(M, Kp, device=dev); Am[:, :K] = A; a_ms, a_ks = Kp, 1
+      if b_mn:
+        Bm = torch.zeros(K, Np, device=dev); Bm[:, :N] = B.t(); b_ns, b_ks = 1, Np
+      else:
+        Bm = torch.zeros(N, Kp, device=dev); Bm[:, :K] = B; b_ns, b_ks = Kp, 1
+      C = torch.full((M, Np), float("nan"), device=dev)
+      _lib.gemm(M, N, K, Am, a_ms, a_ks, Bm, b_ns, b_ks, C, Np, bias=bias, precision=_lib.PREC_TF32)
+      torch.cuda.synchronize()
+      e_t, e = H.rel_err(C[:, :N], ref_t), H.rel_err(C[:, :N], ref)
+      print("tf32 gemm %dx%dx%d a_mn=%d b_mn=%d: err vs truncated %.2e, vs exact %.2e" % (M, N, K, a_mn, b_mn, e_t, e))
+      assert e < 3e-3, (a_mn, b_mn, e)
+      assert e_t < 1e-3 or e < 1e-3, (a_mn, b_mn, e_t)
+
+
+def test_gemm_tf32_epilogues_and_splitk(dev):
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(21)
+  M, N, K = 384, 256, 128
+  A = torch.randn(M, K, generator=g).to(dev)
+  B = torch.randn(N, K, generator=g).to(dev)
+  bias = torch.randn(N, generator=g).to(dev)
+  add = torch.randn(M, N, generator=g).to(dev)
+  At, Bt = _tf32_trunc(A), _tf32_trunc(B)
+  u_ref = _ref_gemm(At, Bt, bias, add)
+  f, u = torch.empty(M, N, device=dev), torch.empty(M, N, device=dev)
+  _lib.gemm(M, N, K, A, K, 1, B, K, 1, f, N, bias=bias, add=add, epilogue=_lib.EPI_GELU, aux=u,
+            precision=_lib.PREC_TF32)
+  assert H.rel_err(u, u_ref) < 1e-4 and H.rel_err(f, O.gelu(u_ref)) < 1e-4
+  dg = torch.empty(M, N, device=dev)
+  _lib.gemm(M, N, K, A, K, 1, B, K, 1, dg, N, epilogue=_lib.EPI_DGELU, aux=u, precision=_lib.PREC_TF32)
+  ur = u_ref.clone().requires_grad_(True)
+  O.gelu(ur).sum().backward()
+  assert H.rel_err(dg, _ref_gemm(At, Bt) * ur.grad) < 1e-4
+  # row remap (ReduceDim -> token slots)
+  Bb, T, Sx, dd, din = 8, 30, 63, 512, 300
+  x = torch.randn(Bb * T, din, generator=g).to(dev)
+  W = torch.randn(dd, din, generator=g).to(dev)
+  proj = torch.zeros(Bb * Sx, dd, device=dev)
+  _lib.gemm(Bb * T, dd, din, x, din, 1, W, din, 1, proj, dd, c_off=2 * dd, c_mb=T, c_mbs=Sx * dd,
+            precision=_lib.PREC_TF32)
+  ref = _ref_gemm(_tf32_trunc(x), _tf32_trunc(W)).view(Bb, T, dd)
+  assert H.rel_err(proj.view(Bb, Sx, dd)[:, 2:2 + T], ref) < 1e-4
+  assert float(proj.view(Bb, Sx, dd)[:, :2].abs().max()) == 0.0
+  # split-K weight gradient: dW [512, 3072] = dY^T X over 13952 rows (both operands MN-major)
+  Kl = 13952
+  dY = torch.randn(Kl, 512, generator=g).to(dev)
+  X = torch.randn(Kl, 3072, generator=g).to(dev)
+  dW = torch.empty(512, 3072, device=dev)
+  _lib.gemm(512, 3072, Kl, dY, 1, 512, X, 1, 3072, dW, 3072, precision=_lib.PREC_TF32, split_k=True)
+  assert H.rel_err(dW, _tf32_trunc(dY).double().t() @ _tf32_trunc(X).double()) < 1e-4
+  dW2 = torch.empty(512, 512, device=dev)
+  _lib.gemm(512, 512, Kl, dY, 1, 512, X, 1, 3072, dW2, 512, precision=_lib.PREC_TF32, split_k=True)
+  assert H.rel_err(dW2, _tf32_trunc(dY).double().t() @ _tf32_trunc(X[:, :512]).double()) < 1e-4
+
+
+def test_train_step_parity_tf32_tensor_core_path(dev):
+  """The performance configuration: all encoder linear layers on the tcgen05 tf32 path.
+  BASELINE.json tolerance: 1e-3 relative fp32 on the outputs."""
+  from mmt_b200 import _lib
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  ed, vb, P, batch, cfg = H.make_case(["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"], 8,
+                                      30, layers=4)
+  Pr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+        for k, v in P.items()}
+  ref = O.cenet_forward(Pr, batch, cfg, training=True, out="conf", text_feat=batch["text_feat"])
+  loss_ref = O.max_margin_ranking_loss(ref["cross_view_conf_matrix"], 0.05, True)
+  loss_ref.backward()
+  net = H.build_cuda_net(ed, vb, P, batch).train()
+  net.cfg.precision = _lib.PREC_TF32
+  out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]
+  loss = MaxMarginRankingLoss(0.05, True)(out)
+  loss.backward()
+  e_conf, e_l2 = H.rel_err(out, ref["cross_view_conf_matrix"]), H.rel_l2(out, ref["cross_view_conf_matrix"])
+  e_loss = abs(float(loss) - float(loss_ref)) / abs(float(loss_ref))
+  gmax = max(float(p.grad.abs().max()) for p in Pr.values() if getattr(p, "grad", None) is not None)
+  worst = ("", 0.0)
+  for name, pr in Pr.items():
+    if not (pr.is_floating_point() and pr.requires_grad) or pr.grad is None:
+      continue
+    scale = max(float(pr.grad.abs().max()), 1e-2 * gmax)
+    err = float((net._param(name).grad.cpu().double() - pr.grad.double()).abs().max()) / scale
+    if err > worst[1]:
+      worst = (name, err)
+  print("tf32 path: conf max-rel %.2e rel-L2 %.2e, loss rel %.2e, worst grad %s %.2e" %
+        (e_conf, e_l2, e_loss, worst[0], worst[1]))
+  assert e_conf < TOL and e_l2 < TOL and e_loss < TOL
+  assert worst[1] < 1e-2, worst
