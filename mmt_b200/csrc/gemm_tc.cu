@@ -28,6 +28,7 @@ constexpr int BK = 32;                 // 32 fp32 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 8;              // tf32: 32 B of K per instruction
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 192;
+constexpr float kTf32TruncComp = 1.0f + 2.0f * 0.7213475f / 2048.0f;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;   // bounded mbarrier spin: a protocol bug traps, never hangs
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -101,14 +102,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms; K-major operands),
+//              1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, 4-row period) -- the only layout the
+//                  tensor core accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address  [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading byte offset [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset  [32,46)
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -189,11 +194,14 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); k-step = +32 B inside the row
-      // MN-major : 32-element (128 B) chunks of m/n, chunks BK*128 B apart (LBO); k-step = one
-      //            8-row group = +1024 B
-      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
-      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
+      // K-major  : rows (m/n) of 128 B = 32 k, SWIZZLE_128B, 8-row groups 1024 B apart (SBO);
+      //            k-step (8 k) = +32 B inside the row
+      // MN-major : rows (k) of 128 B = 32 m/n, SWIZZLE_128B_BASE32B (4-row swizzle period), 4-row
+      //            k-groups 512 B apart (SBO), 32-element m/n chunks BK*128 B apart (LBO);
+      //            k-step (8 k) = 8 rows = +1024 B
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = A_MN ? 512 : 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
+      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = B_MN ? 512 : 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
+      constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -203,8 +211,8 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         const uint32_t sb = sa + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * A_STEP, A_LBO, A_SBO);
-          const uint64_t db = make_smem_desc(sb + k * B_STEP, B_LBO, B_SBO);
+          const uint64_t da = make_smem_desc(sa + k * A_STEP, A_LBO, A_SBO, A_LT);
+          const uint64_t db = make_smem_desc(sb + k * B_STEP, B_LBO, B_SBO, B_LT);
           umma_tf32(tmem_acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);          // smem stage reusable once these MMAs have read it
@@ -319,7 +327,9 @@ int make_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, i
   else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; }
   strides[0] = (cuuint64_t)ld * 4;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
   return 0;
@@ -352,6 +362,13 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(d.K >= 1, MMT_E_SHAPE, "gemm_tc: K=%d", d.K);
   constexpr int BN = 128;
   TcArgs args{d, 1, (d.K + BK - 1) / BK};
+  // kind::tf32 TRUNCATES the 13 low mantissa bits of both fp32 operands (verified against a
+  // bit-truncating fp64 emulation in tests/test_gpu_parity.py), which shrinks every product by
+  // E[dA] + E[dB] with E[d] = 2^-11 * E[2^e/|x|] = 0.7213 * 2^-11 for log-uniform mantissas.
+  // Scaling the accumulator by (1 + 2 * 0.7213 * 2^-11) removes that systematic bias and leaves
+  // the same zero-mean error a round-to-nearest tf32 conversion would (tf32-RN keeps
+  // the similarity matrix inside the 1e-3 bar; plain truncation does not).
+  args.d.alpha = d.alpha * kTf32TruncComp;
   const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
   const int num_kb = (d.K + BK - 1) / BK;
   if ((d.flags & MMT_GEMM_SPLIT_K) && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&

@@ -130,19 +130,19 @@ def test_res_ln_fwd_bwd_matches_torch(dev):
   tr, rr, gr, br = (x.double().requires_grad_(True) for x in (t, r, gamma, beta))
   y_ref = torch.nn.functional.layer_norm(tr + rr, (d,), gr, br, 1e-12)
   y_ref.backward((dy + dy2).double())
-  td, rd = t.to(dev), r.to(dev)
+  td, rd, gd, bd, dyd, dy2d = (x.to(dev) for x in (t, r, gamma, beta, dy, dy2))   # keep references alive
   y = torch.empty(rows, d, device=dev)
   mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
-  _lib.check(lib.mmt_res_ln_fwd(_lib.ptr(td), _lib.ptr(rd), _lib.ptr(gamma.to(dev)),
-                                _lib.ptr(beta.to(dev)), rows, d, 1e-12, 0.0, 0, 0, _lib.ptr(y),
+  _lib.check(lib.mmt_res_ln_fwd(_lib.ptr(td), _lib.ptr(rd), _lib.ptr(gd),
+                                _lib.ptr(bd), rows, d, 1e-12, 0.0, 0, 0, _lib.ptr(y),
                                 _lib.ptr(mean), _lib.ptr(rstd), _lib.stream_ptr()), "res_ln_fwd")
   e_y, e_z = H.rel_err(y, y_ref), H.rel_err(td, t.double() + r.double())
   assert e_y < 1e-5, e_y
   assert e_z < 1e-6, e_z                                         # z written in place
   dz = torch.empty(rows, d, device=dev)
   dgam, dbet, dbias = (torch.zeros(d, device=dev) for _ in range(3))
-  _lib.check(lib.mmt_res_ln_bwd(_lib.ptr(dy.to(dev)), _lib.ptr(dy2.to(dev)), _lib.ptr(td),
-                                _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma.to(dev)), rows, d,
+  _lib.check(lib.mmt_res_ln_bwd(_lib.ptr(dyd), _lib.ptr(dy2d), _lib.ptr(td),
+                                _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gd), rows, d,
                                 0.0, 0, 0, _lib.ptr(dz), None, _lib.ptr(dgam), _lib.ptr(dbet),
                                 _lib.ptr(dbias), _lib.stream_ptr()), "res_ln_bwd")
   errs = [H.rel_err(dz, tr.grad), H.rel_err(dgam, gr.grad), H.rel_err(dbet, br.grad),
@@ -165,7 +165,8 @@ def test_softmax_mask_fwd_bwd(dev):
   dP = torch.randn(B, Hh, S, Sp, generator=g)
   p_ref.backward(dP[..., :S].double())
   P = sc.to(dev)
-  _lib.check(lib.mmt_softmax_mask_fwd(_lib.ptr(P), _lib.ptr(mask.to(dev)), B, Hh, S, Sp, scale, 0.0,
+  maskd = mask.to(dev)
+  _lib.check(lib.mmt_softmax_mask_fwd(_lib.ptr(P), _lib.ptr(maskd), B, Hh, S, Sp, scale, 0.0,
                                       0, 0, _lib.ptr(P), None, _lib.stream_ptr()), "softmax_fwd")
   assert H.rel_err(P[..., :S], p_ref) < 1e-5
   assert float(P[..., S:].abs().max()) == 0.0
@@ -279,7 +280,8 @@ def test_adam_matches_torch(dev):
     gr = torch.randn(n, generator=g)
     pr.grad = gr.clone()
     opt.step()
-    _lib.check(lib.mmt_adam_step(_lib.ptr(p), _lib.ptr(gr.to(dev)), _lib.ptr(m), _lib.ptr(v), n, 5e-5,
+    grd = gr.to(dev)
+    _lib.check(lib.mmt_adam_step(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), n, 5e-5,
                                  0.9, 0.999, 1e-8, 0.01, step, 1.0, _lib.stream_ptr()), "adam")
   assert float((p.cpu() - pr.detach()).abs().max()) < 1e-6
 
@@ -417,6 +419,9 @@ def _tf32_trunc(x):
   return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep 10 mantissa bits
 
 
+TF32_COMP = 1.0 + 2.0 * 0.7213475 / 2048.0     # truncation-bias compensation (mmt_b200/csrc/gemm_tc.cu)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (256, 384, 512), (200, 100, 300),
                                    (13952, 512, 512), (1000, 3072, 512)])
 def test_gemm_tf32_all_operand_layouts(dev, M, N, K):
@@ -430,7 +435,7 @@ def test_gemm_tf32_all_operand_layouts(dev, M, N, K):
   B = torch.randn(N, K, generator=g).to(dev)
   bias = torch.randn(N, generator=g).to(dev)
   ref = _ref_gemm(A, B, bias)
-  ref_t = _ref_gemm(_tf32_trunc(A), _tf32_trunc(B), bias)
+  ref_t = _ref_gemm(_tf32_trunc(A), _tf32_trunc(B)) * TF32_COMP + bias.double()
   for a_mn in (False, True):
     for b_mn in (False, True):
       if a_mn:
@@ -459,7 +464,7 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   bias = torch.randn(N, generator=g).to(dev)
   add = torch.randn(M, N, generator=g).to(dev)
   At, Bt = _tf32_trunc(A), _tf32_trunc(B)
-  u_ref = _ref_gemm(At, Bt, bias, add)
+  u_ref = _ref_gemm(At, Bt) * TF32_COMP + bias.double() + add.double()
   f, u = torch.empty(M, N, device=dev), torch.empty(M, N, device=dev)
   _lib.gemm(M, N, K, A, K, 1, B, K, 1, f, N, bias=bias, add=add, epilogue=_lib.EPI_GELU, aux=u,
             precision=_lib.PREC_TF32)
@@ -468,7 +473,7 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   _lib.gemm(M, N, K, A, K, 1, B, K, 1, dg, N, epilogue=_lib.EPI_DGELU, aux=u, precision=_lib.PREC_TF32)
   ur = u_ref.clone().requires_grad_(True)
   O.gelu(ur).sum().backward()
-  assert H.rel_err(dg, _ref_gemm(At, Bt) * ur.grad) < 1e-4
+  assert H.rel_err(dg, _ref_gemm(At, Bt) * TF32_COMP * ur.grad) < 1e-4
   # row remap (ReduceDim -> token slots)
   Bb, T, Sx, dd, din = 8, 30, 63, 512, 300
   x = torch.randn(Bb * T, din, generator=g).to(dev)
@@ -476,7 +481,7 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   proj = torch.zeros(Bb * Sx, dd, device=dev)
   _lib.gemm(Bb * T, dd, din, x, din, 1, W, din, 1, proj, dd, c_off=2 * dd, c_mb=T, c_mbs=Sx * dd,
             precision=_lib.PREC_TF32)
-  ref = _ref_gemm(_tf32_trunc(x), _tf32_trunc(W)).view(Bb, T, dd)
+  ref = (_ref_gemm(_tf32_trunc(x), _tf32_trunc(W)) * TF32_COMP).view(Bb, T, dd)
   assert H.rel_err(proj.view(Bb, Sx, dd)[:, 2:2 + T], ref) < 1e-4
   assert float(proj.view(Bb, Sx, dd)[:, :2].abs().max()) == 0.0
   # split-K weight gradient: dW [512, 3072] = dY^T X over 13952 rows (both operands MN-major)
@@ -485,10 +490,10 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   X = torch.randn(Kl, 3072, generator=g).to(dev)
   dW = torch.empty(512, 3072, device=dev)
   _lib.gemm(512, 3072, Kl, dY, 1, 512, X, 1, 3072, dW, 3072, precision=_lib.PREC_TF32, split_k=True)
-  assert H.rel_err(dW, _tf32_trunc(dY).double().t() @ _tf32_trunc(X).double()) < 1e-4
+  assert H.rel_err(dW, TF32_COMP * (_tf32_trunc(dY).double().t() @ _tf32_trunc(X).double())) < 1e-4
   dW2 = torch.empty(512, 512, device=dev)
   _lib.gemm(512, 512, Kl, dY, 1, 512, X, 1, 3072, dW2, 512, precision=_lib.PREC_TF32, split_k=True)
-  assert H.rel_err(dW2, _tf32_trunc(dY).double().t() @ _tf32_trunc(X[:, :512]).double()) < 1e-4
+  assert H.rel_err(dW2, TF32_COMP * (_tf32_trunc(dY).double().t() @ _tf32_trunc(X[:, :512]).double())) < 1e-4
 
 
 def test_train_step_parity_tf32_tensor_core_path(dev):
