@@ -351,41 +351,57 @@ __global__ void __launch_bounds__(256) max_margin_kernel(const float* __restrict
   float lsum = 0.f;
   const int i_begin = blockIdx.y * rows_per_block;
   const int i_end = min(n, i_begin + rows_per_block);
-  for (int i = i_begin; i < i_end; ++i) {
-    const float dii = __ldg(x + (int64_t)i * n + i);
-    float xv[4] = {0.f, 0.f, 0.f, 0.f}, g[4];
-    if (j0 < n) {
-      if (vec) {
-        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)i * n + j0);
-        xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
-      } else {
+  constexpr int RU = 4;                          // rows in flight per thread (memory-level parallelism)
+  for (int ib = i_begin; ib < i_end; ib += RU) {
+    float dii[RU];
+    float4 xr[RU];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (j0 + q < n) xv[q] = x[(int64_t)i * n + j0 + q];
-      }
-    }
-    float rowcnt = 0.f;
+    for (int r = 0; r < RU; ++r) {
+      const int i = ib + r;
+      dii[r] = (i < i_end) ? __ldg(x + (int64_t)i * n + i) : 0.f;
+      xr[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < i_end && j0 < n) {
+        if (vec) {
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(xr[r].x), "=f"(xr[r].y), "=f"(xr[r].z), "=f"(xr[r].w)
+                       : "l"(x + (int64_t)i * n + j0));
+        } else {
+          float* pv = reinterpret_cast<float*>(&xr[r]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = j0 + q;
-      const bool in = j < n;
-      const float a = margin - dii + xv[q], b = margin - djj[q] + xv[q];
-      const bool off = in && (j != i);
-      const bool use = in && (off || !fix_norm);
-      const float ia = (use && a > 0.f) ? 1.f : 0.f, ib = (use && b > 0.f) ? 1.f : 0.f;
-      lsum += ia * a + ib * b;
-      g[q] = off ? (ia + ib) * inv_cnt : 0.f;
-      if (off) { rowcnt += ia; colcnt[q] += ib; }
-    }
-    if (dx) {
-      if (j0 < n) {
-        if (vec) *reinterpret_cast<float4*>(dx + (int64_t)i * n + j0) = make_float4(g[0], g[1], g[2], g[3]);
-        else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (j0 + q < n) dx[(int64_t)i * n + j0 + q] = g[q];
+          for (int q = 0; q < 4; ++q) if (j0 + q < n) pv[q] = x[(int64_t)i * n + j0 + q];
         }
       }
-      rowcnt = warp_sum(rowcnt);
-      if (lane == 0 && rowcnt != 0.f) atomicAdd(ws + 2 + i, rowcnt);
+    }
+#pragma unroll
+    for (int r = 0; r < RU; ++r) {
+      const int i = ib + r;
+      if (i >= i_end) break;
+      const float xv[4] = {xr[r].x, xr[r].y, xr[r].z, xr[r].w};
+      float g[4];
+      float rowcnt = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        const bool in = j < n;
+        const float a = margin - dii[r] + xv[q], b = margin - djj[q] + xv[q];
+        const bool off = in && (j != i);
+        const bool use = in && (off || !fix_norm);
+        const float ia = (use && a > 0.f) ? 1.f : 0.f, ib2 = (use && b > 0.f) ? 1.f : 0.f;
+        lsum += ia * a + ib2 * b;
+        g[q] = off ? (ia + ib2) * inv_cnt : 0.f;
+        if (off) { rowcnt += ia; colcnt[q] += ib2; }
+      }
+      if (dx) {
+        if (j0 < n) {
+          if (vec) *reinterpret_cast<float4*>(dx + (int64_t)i * n + j0) = make_float4(g[0], g[1], g[2], g[3]);
+          else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (j0 + q < n) dx[(int64_t)i * n + j0 + q] = g[q];
+          }
+        }
+        rowcnt = warp_sum(rowcnt);
+        if (lane == 0 && rowcnt != 0.f) atomicAdd(ws + 2 + i, rowcnt);
+      }
     }
   }
   if (dx) {
