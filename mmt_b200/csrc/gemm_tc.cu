@@ -56,11 +56,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > SPIN_LIMIT) __trap();
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1) {
+// rank-4 tensor maps: {inner, rows-or-k, batch_inner, batch_outer}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -141,7 +142,9 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   const mmt_gemm_desc& d = args.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int ksplit = blockIdx.z;
+  const int ksplit = blockIdx.z % args.split_k;
+  const int z = blockIdx.z / args.split_k;
+  const int z0 = z / d.batch_inner, z1 = z % d.batch_inner;
   const int num_kb_total = (d.K + BK - 1) / BK;
   const int kb_begin = ksplit * args.kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + args.kb_per_split);
@@ -172,18 +175,18 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         uint8_t* sb = sa + A_BYTES;
         const int k0 = (kb_begin + i) * BK;
         if (!A_MN) {
-          tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);                   // box {32 k, 128 m}
+          tma_load_4d(sa, &map_a, &full_bar[s], k0, m0, z1, z0);           // box {32 k, 128 m}
         } else {
 #pragma unroll
           for (int j = 0; j < BM / 32; ++j)                                 // 4 boxes {32 m, 32 k}
-            tma_load_2d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0);
+            tma_load_4d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0, z1, z0);
         }
         if (!B_MN) {
-          tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+          tma_load_4d(sb, &map_b, &full_bar[s], k0, n0, z1, z0);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+            tma_load_4d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0, z1, z0);
         }
       }
     }
@@ -227,10 +230,13 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
     tc_fence_after();
     const bool row_ok = (m < d.M) && (num_kb > 0);
     int64_t row = 0;
-    if (row_ok) row = d.c_mb > 0 ? (int64_t)(m / d.c_mb) * d.c_mbs + (int64_t)(m % d.c_mb) * d.c_ms
-                                 : (int64_t)m * d.c_ms;
+    if (row_ok) row = (int64_t)z0 * d.c_bs0 + (int64_t)z1 * d.c_bs1 +
+                      (d.c_mb > 0 ? (int64_t)(m / d.c_mb) * d.c_mbs + (int64_t)(m % d.c_mb) * d.c_ms
+                                  : (int64_t)m * d.c_ms);
+    const float* bias = d.bias ? d.bias + (int64_t)z * d.bias_bs : nullptr;
     const bool lead = (ksplit == 0);
     const bool vec_ok = ((d.c_ms & 3) == 0) && ((d.c_mbs & 3) == 0) && ((d.N & 3) == 0) &&
+                        (((d.c_bs0 | d.c_bs1 | d.bias_bs) & 3) == 0) &&
                         ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           if (nb + j >= d.N) break;
           float4 o = make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha);
           if (lead || args.split_k == 1) {
-            if (d.bias) {
-              const float4 b = *reinterpret_cast<const float4*>(d.bias + nb + j);
+            if (bias) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + nb + j);
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             if (addrow) {
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           if (nb + j >= d.N) break;
           float o = v[j] * d.alpha;
           if (lead || args.split_k == 1) {
-            if (d.bias) o += d.bias[nb + j];
+            if (bias) o += bias[nb + j];
             if (addrow) o += addrow[j];
           }
           if (args.split_k > 1) { atomicAdd(crow + j, o); continue; }
@@ -315,18 +321,25 @@ EncodeTiledFn get_encode() {
 
 // rows x K operand, element (r, k) at base[r*rs + k*ks] with either ks == 1 (K-major) or rs == 1.
 int make_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
-             int tile_rows, const char* what) {
+             int tile_rows, int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, const char* what) {
   EncodeTiledFn enc = get_encode();
   MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled unavailable");
   const int64_t ld = mn_major ? ks : rs;
   MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0 && ld >= 1, MMT_E_ALIGN,
                 "gemm_tc: operand %s needs a 16-byte aligned base and stride (ld=%lld)", what, (long long)ld);
-  cuuint64_t dims[2], strides[1];
-  cuuint32_t box[2], estr[2] = {1, 1};
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   if (!mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)tile_rows; }
   else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; }
+  dims[2] = (cuuint64_t)batch_inner; dims[3] = (cuuint64_t)batch_outer;
+  box[2] = box[3] = 1;
   strides[0] = (cuuint64_t)ld * 4;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  // a size-1 batch dimension still needs a legal (16-byte multiple) stride
+  strides[1] = (cuuint64_t)((batch_inner > 1 ? bs1 : ld) * 4);
+  strides[2] = (cuuint64_t)((batch_outer > 1 ? bs0 : ld) * 4);
+  MMT_ARG_CHECK(strides[1] % 16 == 0 && strides[2] % 16 == 0, MMT_E_ALIGN,
+                "gemm_tc: operand %s batch strides must be multiples of 4 floats", what);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -345,7 +358,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cud
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     configured = true;
   }
-  dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k);
+  dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k * args.d.batch);
   kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
   MMT_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
@@ -354,7 +367,8 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cud
 }  // namespace
 
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
-  MMT_ARG_CHECK(d.batch == 1, MMT_E_UNSUPPORTED, "gemm_tc: batched problems use MMT_PREC_FP32");
+  MMT_ARG_CHECK(d.batch % d.batch_inner == 0, MMT_E_SHAPE, "gemm_tc: batch %d not a multiple of batch_inner %d",
+                d.batch, d.batch_inner);
   MMT_ARG_CHECK(d.a_kb == 0, MMT_E_UNSUPPORTED, "gemm_tc: two-level K index uses MMT_PREC_FP32");
   const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
   MMT_ARG_CHECK(!a_mn || d.a_ms == 1, MMT_E_UNSUPPORTED, "gemm_tc: A must be contiguous along k or m");
@@ -371,7 +385,7 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   args.d.alpha = d.alpha * kTf32TruncComp;
   const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
   const int num_kb = (d.K + BK - 1) / BK;
-  if ((d.flags & MMT_GEMM_SPLIT_K) && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
+  if ((d.flags & MMT_GEMM_SPLIT_K) && d.batch == 1 && d.c_mb == 0 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
       d.add != d.C && tiles * 2 <= num_sms() && num_kb >= 32) {
     int split = (2 * num_sms() + tiles - 1) / tiles;
     if (split > num_kb / 8) split = num_kb / 8;
@@ -383,9 +397,10 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
     }
   }
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, "A");
+  const int bo = d.batch / d.batch_inner;
+  int rc = make_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, bo, d.batch_inner, d.a_bs0, d.a_bs1, "A");
   if (rc) return rc;
-  rc = make_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, "B");
+  rc = make_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, bo, d.batch_inner, d.b_bs0, d.b_bs1, "B");
   if (rc) return rc;
   if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, args, stream);
   if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, args, stream);

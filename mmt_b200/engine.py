@@ -38,7 +38,8 @@ class Config:
     self.p_txt = float(txt_dropout)
     self.type_idx = type_idx            # list of int per expert (sorted order)
     self.in_dims = [layout.expert_dims[m]["dim"] for m in layout.mods]
-    self.precision = PREC_FP32          # PREC_TF32 once the tcgen05 path is enabled
+    self.precision = PREC_FP32          # linear layers: PREC_TF32 = tcgen05 tensor-core path
+    self.attn_precision = None          # attention matmuls; None -> same as `precision`
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -66,6 +67,7 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   st = stream_ptr()
   lib = _lib.load()
   prec = cfg.precision
+  aprec = cfg.precision if cfg.attn_precision is None else cfg.attn_precision
   p_hid = cfg.p_hidden if training else 0.0
   p_att = cfg.p_attn if training else 0.0
   sv = Saved()
@@ -116,7 +118,7 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
     # K5: scores = Q K^T per (b, h) (bert.py:147)
     P = _empty((B, H, S, Sp), flat)
     gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=B * H, batch_inner=H,
-         a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(H * S * Sp, S * Sp), precision=PREC_FP32)
+         a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(H * S * Sp, S * Sp), precision=aprec)
     Pd = _empty((B, H, S, Sp), flat) if p_att > 0 else P
     check(lib.mmt_softmax_mask_fwd(ptr(P), ptr(sv.mask), B, H, S, Sp, scale, p_att, seed,
                                    SITE_LAYER + 4 * l, ptr(P), ptr(Pd) if p_att > 0 else None, st),
@@ -124,7 +126,7 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
     # ctx = P V, heads merged by the output addressing (bert.py:166-170)
     ctx = _empty((BS, d), flat)
     gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx, d, b_off=2 * d, batch=B * H, batch_inner=H,
-         a_bs=(H * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh), precision=PREC_FP32)
+         a_bs=(H * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh), precision=aprec)
     # K6: attention output dense + dropout + residual + LN (bert.py:186-188)
     z1 = _empty((BS, d), flat)
     gemm(BS, d, d, ctx, d, 1, flat, d, 1, z1, d, b_off=L.off(p + "attention.output.dense.weight"),
@@ -290,6 +292,7 @@ def video_backward(cfg, flat, gflat, sv, dvid):
   st = stream_ptr()
   lib = _lib.load()
   prec = cfg.precision
+  aprec = cfg.precision if cfg.attn_precision is None else cfg.attn_precision
   seed = sv.seed
   scale = 1.0 / math.sqrt(dh)
 
@@ -347,17 +350,17 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     bsQ = (S * 3 * d, dh)
     # dP = dctx @ V^T
     gemm(S, S, dh, dctx, d, 1, ls.qkv, 3 * d, 1, dP, Sp, b_off=2 * d, batch=B * H, batch_inner=H,
-         a_bs=(S * d, dh), b_bs=bsQ, c_bs=bsP)
+         a_bs=(S * d, dh), b_bs=bsQ, c_bs=bsP, precision=aprec)
     # dV = Pd^T @ dctx
     gemm(S, dh, S, ls.Pd, 1, Sp, dctx, 1, d, dqkv, 3 * d, c_off=2 * d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=(S * d, dh), c_bs=bsQ)
+         a_bs=bsP, b_bs=(S * d, dh), c_bs=bsQ, precision=aprec)
     check(lib.mmt_softmax_mask_bwd(ptr(dP), ptr(ls.P), B, H, S, Sp, scale, p_att, seed,
                                    SITE_LAYER + 4 * l, st), "mmt_softmax_mask_bwd")
     # dQ = dS @ K ; dK = dS^T @ Q
     gemm(S, dh, S, dP, Sp, 1, ls.qkv, 1, 3 * d, dqkv, 3 * d, b_off=d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=bsQ, c_bs=bsQ)
+         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec)
     gemm(S, dh, S, dP, 1, Sp, ls.qkv, 1, 3 * d, dqkv, 3 * d, c_off=d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=bsQ, c_bs=bsQ)
+         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec)
     # QKV projection: dWqkv [3d, d] = dqkv^T @ h_in ; dbqkv ; dh = dz1 + dqkv @ Wqkv
     gemm(3 * d, d, BS, dqkv, 1, 3 * d, ls.h_in, 1, d, gflat, d,
          c_off=L.off(p + "attention.self.query.weight"), precision=prec, split_k=True)

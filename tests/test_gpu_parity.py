@@ -496,9 +496,54 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   assert H.rel_err(dW2, TF32_COMP * (_tf32_trunc(dY).double().t() @ _tf32_trunc(X[:, :512]).double())) < 1e-4
 
 
-def test_train_step_parity_tf32_tensor_core_path(dev):
-  """The performance configuration: all encoder linear layers on the tcgen05 tf32 path.
-  BASELINE.json tolerance: 1e-3 relative fp32 on the outputs."""
+def test_gemm_tf32_batched_attention_layouts(dev):
+  """The six attention matmuls (scores, context and their four backward products) as batched
+  tcgen05 GEMMs over (b, h) with head-strided operands (rank-4 TMA maps)."""
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(33)
+  Bt, Hh, S, dh = 3, 4, 218, 128
+  d = Hh * dh
+  Sp = (S + 3) // 4 * 4
+  qkv = torch.randn(Bt * S, 3 * d, generator=g).to(dev)
+  q = qkv[:, :d].view(Bt, S, Hh, dh).permute(0, 2, 1, 3)
+  k = qkv[:, d:2 * d].view(Bt, S, Hh, dh).permute(0, 2, 1, 3)
+  v = qkv[:, 2 * d:].view(Bt, S, Hh, dh).permute(0, 2, 1, 3)
+  tq, tk, tv = (_tf32_trunc(x.contiguous()).double() for x in (q, k, v))
+  bsP, bsQ = (Hh * S * Sp, S * Sp), (S * 3 * d, dh)
+  kw = dict(batch=Bt * Hh, batch_inner=Hh, precision=_lib.PREC_TF32)
+  P = torch.zeros(Bt, Hh, S, Sp, device=dev)
+  _lib.gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, a_bs=bsQ, b_bs=bsQ, c_bs=bsP, **kw)
+  assert H.rel_err(P[..., :S], TF32_COMP * (tq @ tk.transpose(-1, -2))) < 1e-4
+  Pn = torch.softmax(torch.randn(Bt, Hh, S, Sp, generator=g), -1).to(dev)
+  Pn[..., S:] = 0
+  tP = _tf32_trunc(Pn).double()[..., :S]
+  ctx = torch.zeros(Bt * S, d, device=dev)
+  _lib.gemm(S, dh, S, Pn, Sp, 1, qkv, 1, 3 * d, ctx, d, b_off=2 * d, a_bs=bsP, b_bs=bsQ, c_bs=(S * d, dh), **kw)
+  ref = (TF32_COMP * (tP @ tv)).permute(0, 2, 1, 3).reshape(Bt * S, d)
+  assert H.rel_err(ctx, ref) < 1e-4
+  dctx = torch.randn(Bt * S, d, generator=g).to(dev)
+  tdc = _tf32_trunc(dctx).double().view(Bt, S, Hh, dh).permute(0, 2, 1, 3)
+  dP = torch.zeros(Bt, Hh, S, Sp, device=dev)
+  _lib.gemm(S, S, dh, dctx, d, 1, qkv, 3 * d, 1, dP, Sp, b_off=2 * d, a_bs=(S * d, dh), b_bs=bsQ, c_bs=bsP, **kw)
+  assert H.rel_err(dP[..., :S], TF32_COMP * (tdc @ tv.transpose(-1, -2))) < 1e-4
+  dqkv = torch.zeros(Bt * S, 3 * d, device=dev)
+  _lib.gemm(S, dh, S, Pn, 1, Sp, dctx, 1, d, dqkv, 3 * d, c_off=2 * d, a_bs=bsP, b_bs=(S * d, dh), c_bs=bsQ, **kw)
+  _lib.gemm(S, dh, S, Pn, Sp, 1, qkv, 1, 3 * d, dqkv, 3 * d, b_off=d, a_bs=bsP, b_bs=bsQ, c_bs=bsQ, **kw)
+  _lib.gemm(S, dh, S, Pn, 1, Sp, qkv, 1, 3 * d, dqkv, 3 * d, c_off=d, a_bs=bsP, b_bs=bsQ, c_bs=bsQ, **kw)
+
+  def heads(x):
+    return x.view(Bt, S, Hh, dh).permute(0, 2, 1, 3)
+
+  assert H.rel_err(heads(dqkv[:, 2 * d:]), TF32_COMP * (tP.transpose(-1, -2) @ tdc)) < 1e-4
+  assert H.rel_err(heads(dqkv[:, :d]), TF32_COMP * (tP @ tk)) < 1e-4
+  assert H.rel_err(heads(dqkv[:, d:2 * d]), TF32_COMP * (tP.transpose(-1, -2) @ tq)) < 1e-4
+
+
+@pytest.mark.parametrize("attn", ["fp32", "tf32"])
+def test_train_step_parity_tf32_tensor_core_path(dev, attn):
+  """The performance configuration: all encoder linear layers (and, for attn='tf32', the
+  attention matmuls) on the tcgen05 tf32 path.  BASELINE.json tolerance: 1e-3 relative fp32 on
+  the outputs."""
   from mmt_b200 import _lib
   from mmt_b200.model.loss import MaxMarginRankingLoss
   ed, vb, P, batch, cfg = H.make_case(["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"], 8,
@@ -510,6 +555,7 @@ def test_train_step_parity_tf32_tensor_core_path(dev):
   loss_ref.backward()
   net = H.build_cuda_net(ed, vb, P, batch).train()
   net.cfg.precision = _lib.PREC_TF32
+  net.cfg.attn_precision = _lib.PREC_TF32 if attn == "tf32" else _lib.PREC_FP32
   out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]
   loss = MaxMarginRankingLoss(0.05, True)(out)
   loss.backward()
@@ -524,7 +570,7 @@ def test_train_step_parity_tf32_tensor_core_path(dev):
     err = float((net._param(name).grad.cpu().double() - pr.grad.double()).abs().max()) / scale
     if err > worst[1]:
       worst = (name, err)
-  print("tf32 path: conf max-rel %.2e rel-L2 %.2e, loss rel %.2e, worst grad %s %.2e" %
-        (e_conf, e_l2, e_loss, worst[0], worst[1]))
+  print("tf32 path (attention %s): conf max-rel %.2e rel-L2 %.2e, loss rel %.2e, worst grad %s %.2e" %
+        (attn, e_conf, e_l2, e_loss, worst[0], worst[1]))
   assert e_conf < TOL and e_l2 < TOL and e_loss < TOL
   assert worst[1] < 1e-2, worst
