@@ -90,9 +90,10 @@ int mmt_colsum(const float* X, int64_t rows, int32_t n, int64_t ld, int32_t rb, 
 
 /* ---------------------------------------------------------------------------------------------
  * Token assembly + BertEmbeddings  (model/model.py:485-567 + model/bert.py:87-105), one kernel.
- * proj   [B*S, d]   raw ReduceDim GEMM outputs already sitting in their token slots (CLS rows are
- *                   ignored); this kernel L2-normalises them (model.py:725, eps 1e-12), adds
- *                   position/type embeddings, LayerNorms and applies dropout.
+ * proj   [M, B, T+1, d]  raw ReduceDim GEMM outputs, expert-major: row (k, b, 0) is the projected
+ *                   max-pooled feature ([AGG] token), rows (k, b, 1..T) the projected frames.
+ *                   This kernel gathers them into token order, L2-normalises (model.py:725, eps
+ *                   1e-12), adds position/type embeddings, LayerNorms and applies dropout.
  * ft,ind [M,B,T]    features_t / features_ind per expert (sorted expert order).
  * type_idx [M]      int32 token-type id per expert (utils/util.py:154-247).
  * Outputs: h [B*S,d]; mask [B*S] (1 = attend); pos_ids,type_ids [B*S] int32; inv_norm [B*S];
@@ -104,12 +105,12 @@ int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const
                      int32_t max_pos, float eps, float p_drop, uint64_t seed, uint32_t site,
                      float* h, float* mask, int32_t* pos_ids, int32_t* type_ids, float* inv_norm,
                      float* mean, float* rstd, void* stream);
-/* Backward of the above: dh -> dproj (gradient w.r.t. the raw GEMM outputs, CLS rows zero) and
- * ACCUMULATES into dpos_emb [max_pos,d], dtype_emb [type_vocab,d], dgamma, dbeta [d]. */
+/* Backward of the above: dh [B*S,d] -> dproj [M,B,T+1,d] (gradient w.r.t. the raw GEMM outputs)
+ * and ACCUMULATES into dpos_emb [max_pos,d], dtype_emb [type_vocab,d], dgamma, dbeta [d]. */
 int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
                      const int32_t* type_ids, const float* inv_norm, const float* mean,
                      const float* rstd, const float* pos_emb, const float* type_emb,
-                     const float* gamma, int32_t B, int32_t S, int32_t d, float p_drop,
+                     const float* gamma, int32_t B, int32_t M, int32_t T, int32_t d, float p_drop,
                      uint64_t seed, uint32_t site, float* dproj, float* dpos_emb,
                      float* dtype_emb, float* dgamma, float* dbeta, void* stream);
 
@@ -176,10 +177,12 @@ int mmt_geu_gate_bwd(const float* dE, const float* X, const float* G, const floa
 /* Elementwise dropout out = mask * in / (1-p) (moe_txt_dropout, model/model.py:274). */
 int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, uint64_t seed,
                 uint32_t site, void* stream);
-/* Text mixture weights (model/model.py:276-281, 618): w = L1norm(softmax(logits)) over M <= 32. */
-int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, float* w, void* stream);
-int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, float* dlogits,
-                        void* stream);
+/* Text mixture weights (model/model.py:276-281, 618): w [R,M] = L1norm(softmax(logits)) over
+ * M <= 32; logits / dlogits rows are `ld` floats apart (ld >= M; padding columns of dlogits are
+ * written as 0 so the padded matrix can feed the tensor-core GEMMs). */
+int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, int32_t ld, float* w, void* stream);
+int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, int32_t ld,
+                        float* dlogits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * sharded_cross_view_inner_product (model/model.py:789-837) given the per-expert dot products

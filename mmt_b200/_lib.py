@@ -48,7 +48,7 @@ SIGNATURES = {
     "mmt_gemm": (c_i32, [ctypes.POINTER(GemmDesc), c_p]),
     "mmt_colsum": (c_i32, [c_p, c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p]),
     "mmt_embed_ln_fwd": (c_i32, [c_p] * 8 + [c_i32] * 5 + [c_f, c_f, c_u64, c_u32] + [c_p] * 7 + [c_p]),
-    "mmt_embed_ln_bwd": (c_i32, [c_p] * 10 + [c_i32] * 3 + [c_f, c_u64, c_u32] + [c_p] * 5 + [c_p]),
+    "mmt_embed_ln_bwd": (c_i32, [c_p] * 10 + [c_i32] * 4 + [c_f, c_u64, c_u32] + [c_p] * 5 + [c_p]),
     "mmt_res_ln_fwd": (c_i32, [c_p] * 4 + [c_i64, c_i32, c_f, c_f, c_u64, c_u32] + [c_p] * 3 + [c_p]),
     "mmt_res_ln_bwd": (c_i32, [c_p] * 6 + [c_i64, c_i32, c_f, c_u64, c_u32] + [c_p] * 5 + [c_p]),
     "mmt_softmax_mask_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p, c_p, c_p]),
@@ -58,8 +58,8 @@ SIGNATURES = {
     "mmt_geu_gate_fwd": (c_i32, [c_p] * 6 + [c_i32] * 4 + [c_f, c_f] + [c_p] * 6 + [c_p]),
     "mmt_geu_gate_bwd": (c_i32, [c_p] * 11 + [c_i32] * 4 + [c_p] * 4 + [c_p]),
     "mmt_dropout": (c_i32, [c_p, c_p, c_i64, c_i32, c_f, c_u64, c_u32, c_p]),
-    "mmt_moe_softmax_fwd": (c_i32, [c_p, c_i32, c_i32, c_p, c_p]),
-    "mmt_moe_softmax_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_p, c_p]),
+    "mmt_moe_softmax_fwd": (c_i32, [c_p, c_i32, c_i32, c_i32, c_p, c_p]),
+    "mmt_moe_softmax_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
     "mmt_sims_combine_fwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
     "mmt_sims_combine_bwd": (c_i32, [c_p] * 4 + [c_i32] * 5 + [c_p, c_p, c_p]),
     "mmt_max_margin_fwd_bwd": (c_i32, [c_p, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p]),

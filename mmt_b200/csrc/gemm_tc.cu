@@ -247,46 +247,67 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       float* crow = d.C + row + nb;
       const float* addrow = d.add ? d.add + row + nb : nullptr;
       float* auxrow = d.aux ? d.aux + row + nb : nullptr;
-      if (vec_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (nb + j >= d.N) break;
-          float4 o = make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha);
-          if (lead || args.split_k == 1) {
-            if (bias) {
+      for (int j = 0; j < 32; j += 4) {
+        // one group of 4 columns: 128-bit accesses when the whole group is in range and aligned,
+        // predicated scalars otherwise (everything is statically indexed: no local-memory spill)
+        const bool full = vec_ok && (nb + j + 4 <= d.N);
+        float o[4] = {v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha};
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ok[q] = (nb + j + q < d.N);
+        if (lead || args.split_k == 1) {
+          if (bias) {
+            if (full) {
               const float4 b = *reinterpret_cast<const float4*>(bias + nb + j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (ok[q]) o[q] += bias[nb + j + q];
             }
-            if (addrow) {
+          }
+          if (addrow) {
+            if (full) {
               const float4 a = *reinterpret_cast<const float4*>(addrow + j);
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (ok[q]) o[q] += addrow[j + q];
             }
           }
-          if (args.split_k > 1) {
-            atomicAdd(reinterpret_cast<float4*>(crow + j), o);
-            continue;
-          }
-          if (d.epilogue == MMT_EPI_GELU) {
-            *reinterpret_cast<float4*>(auxrow + j) = o;
-            o = make_float4(gelu_erf(o.x), gelu_erf(o.y), gelu_erf(o.z), gelu_erf(o.w));
-          } else if (d.epilogue == MMT_EPI_DGELU) {
-            const float4 u = *reinterpret_cast<const float4*>(auxrow + j);
-            o.x *= dgelu_erf(u.x); o.y *= dgelu_erf(u.y); o.z *= dgelu_erf(u.z); o.w *= dgelu_erf(u.w);
-          }
-          *reinterpret_cast<float4*>(crow + j) = o;
         }
-      } else {
-        for (int j = 0; j < 32; ++j) {
-          if (nb + j >= d.N) break;
-          float o = v[j] * d.alpha;
-          if (lead || args.split_k == 1) {
-            if (bias) o += bias[nb + j];
-            if (addrow) o += addrow[j];
+        if (args.split_k > 1) {
+          if (full) atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(o[0], o[1], o[2], o[3]));
+          else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (ok[q]) atomicAdd(crow + j + q, o[q]);
           }
-          if (args.split_k > 1) { atomicAdd(crow + j, o); continue; }
-          if (d.epilogue == MMT_EPI_GELU) { auxrow[j] = o; o = gelu_erf(o); }
-          else if (d.epilogue == MMT_EPI_DGELU) o *= dgelu_erf(auxrow[j]);
-          crow[j] = o;
+          continue;
+        }
+        if (d.epilogue == MMT_EPI_GELU) {
+          if (full) *reinterpret_cast<float4*>(auxrow + j) = make_float4(o[0], o[1], o[2], o[3]);
+          else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (ok[q]) auxrow[j + q] = o[q];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = gelu_erf(o[q]);
+        } else if (d.epilogue == MMT_EPI_DGELU) {
+          float u[4] = {0.f, 0.f, 0.f, 0.f};
+          if (full) {
+            const float4 t = *reinterpret_cast<const float4*>(auxrow + j);
+            u[0] = t.x; u[1] = t.y; u[2] = t.z; u[3] = t.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (ok[q]) u[q] = auxrow[j + q];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] *= dgelu_erf(u[q]);
+        }
+        if (full) *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (ok[q]) crow[j + q] = o[q];
         }
       }
     }

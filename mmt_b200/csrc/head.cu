@@ -221,12 +221,12 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(float* __restrict__ dG,
 // ------------------------------------------------------------------------------------------
 // text mixture weights: w = L1norm(softmax(logits))   (model/model.py:280-281, 618)
 // ------------------------------------------------------------------------------------------
-__global__ void moe_softmax_fwd_kernel(const float* __restrict__ logits, int R, int M,
+__global__ void moe_softmax_fwd_kernel(const float* __restrict__ logits, int R, int M, int ld,
                                        float* __restrict__ w) {
   const int r = blockIdx.x * blockDim.y + threadIdx.y;
   if (r >= R) return;
   const int lane = threadIdx.x;
-  const float x = lane < M ? logits[(int64_t)r * M + lane] : -INFINITY;
+  const float x = lane < M ? logits[(int64_t)r * ld + lane] : -INFINITY;
   const float mx = warp_max(x);
   const float e = lane < M ? expf(x - mx) : 0.f;
   const float p = e / warp_sum(e);
@@ -235,7 +235,7 @@ __global__ void moe_softmax_fwd_kernel(const float* __restrict__ logits, int R, 
 }
 
 __global__ void moe_softmax_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ w,
-                                       int R, int M, float* __restrict__ dlogits) {
+                                       int R, int M, int ld, float* __restrict__ dlogits) {
   const int r = blockIdx.x * blockDim.y + threadIdx.y;
   if (r >= R) return;
   const int lane = threadIdx.x;
@@ -245,7 +245,7 @@ __global__ void moe_softmax_bwd_kernel(const float* __restrict__ dw, const float
   float g = lane < M ? dw[(int64_t)r * M + lane] : 0.f;
   g = g - warp_sum(g * p);                                // L1-normalise backward: dp = dw - <dw, w>
   const float dot = warp_sum(g * p);
-  if (lane < M) dlogits[(int64_t)r * M + lane] = p * (g - dot);
+  if (lane < ld) dlogits[(int64_t)r * ld + lane] = lane < M ? p * (g - dot) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -509,19 +509,19 @@ int mmt_geu_gate_bwd(const float* dE, const float* X, const float* G, const floa
   return 0;
 }
 
-int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, float* w, void* stream) {
+int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, int32_t ld, float* w, void* stream) {
   MMT_ARG_CHECK(logits && w, MMT_E_ARG, "mmt_moe_softmax_fwd: null pointer");
-  MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0, MMT_E_SHAPE, "mmt_moe_softmax_fwd: M=%d must be in [1,32]", M);
-  moe_softmax_fwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(logits, R, M, w);
+  MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0 && ld >= M && ld <= 32, MMT_E_SHAPE, "mmt_moe_softmax_fwd: M=%d ld=%d must satisfy 1 <= M <= ld <= 32", M, ld);
+  moe_softmax_fwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(logits, R, M, ld, w);
   MMT_LAUNCH_CHECK("moe_softmax_fwd");
   return 0;
 }
 
-int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, float* dlogits,
-                        void* stream) {
+int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, int32_t ld,
+                        float* dlogits, void* stream) {
   MMT_ARG_CHECK(dw && w && dlogits, MMT_E_ARG, "mmt_moe_softmax_bwd: null pointer");
-  MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0, MMT_E_SHAPE, "mmt_moe_softmax_bwd: M=%d must be in [1,32]", M);
-  moe_softmax_bwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(dw, w, R, M, dlogits);
+  MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0 && ld >= M && ld <= 32, MMT_E_SHAPE, "mmt_moe_softmax_bwd: M=%d ld=%d must satisfy 1 <= M <= ld <= 32", M, ld);
+  moe_softmax_bwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(dw, w, R, M, ld, dlogits);
   MMT_LAUNCH_CHECK("moe_softmax_bwd");
   return 0;
 }

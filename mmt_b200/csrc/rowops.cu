@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
         pos = (int)tv;                                       // .long(): truncation
         mk = (float)(long long)indp[j - 1];
       }
-      load_row<VEC>(proj + r * d, lane, e);
+      load_row<VEC>(proj + (((int64_t)k * B + b) * (T + 1) + j) * d, lane, e);   // [M, B, T+1, d]
       float ss = row_dot<VEC>(e, e);
       invn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);            // F.normalize eps (model.py:725)
 #pragma unroll
@@ -93,13 +93,14 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
     const int32_t* __restrict__ pos_ids, const int32_t* __restrict__ type_ids,
     const float* __restrict__ inv_norm, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ pos_emb,
-    const float* __restrict__ type_emb, const float* __restrict__ gamma, int B, int S,
+    const float* __restrict__ type_emb, const float* __restrict__ gamma, int B, int M, int T,
     float p_drop, uint64_t seed, uint32_t site, float* __restrict__ dproj,
     float* __restrict__ dpos_emb, float* __restrict__ dtype_emb, float* __restrict__ dgamma,
     float* __restrict__ dbeta) {
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = 1 + M * (T + 1);
   const int64_t rows = (int64_t)B * S;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   float4 g[VEC], ag[VEC], ab[VEC];
@@ -107,7 +108,9 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
-    const int s = (int)(r % S);
+    const int s = (int)(r % S), b = (int)(r / S);
+    // expert-major row of the projection buffers [M, B, T+1, d] (CLS has none)
+    const int64_t prow = s == 0 ? 0 : (((int64_t)((s - 1) / (T + 1)) * B + b) * (T + 1) + (s - 1) % (T + 1));
     const int pos = pos_ids[r], type = type_ids[r];
     const float invn = inv_norm[r], mean = mean_i[r], rstd = rstd_i[r];
     float4 gy[VEC], f[VEC], xh[VEC], pe[VEC], te[VEC];
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
 #pragma unroll
       for (int i = 0; i < VEC; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      load_row<VEC>(proj + r * d, lane, f);
+      load_row<VEC>(proj + prow * d, lane, f);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) F4_OP(f[i], f[i].x * invn, f[i].y * invn, f[i].z * invn, f[i].w * invn);
     }
@@ -152,10 +155,8 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
       atomic_add4(dpos_emb + (int64_t)pos * d + 4 * (lane + 32 * i), de[i]);
       atomic_add4(dtype_emb + (int64_t)type * d + 4 * (lane + 32 * i), de[i]);
     }
-    if (s == 0) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) de[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else if (invn < 1e12f) {                           // normalize backward: (I - f f^T) de / ||y||
+    if (s == 0) continue;                                // [CLS] carries no projected feature
+    if (invn < 1e12f) {                           // normalize backward: (I - f f^T) de / ||y||
       const float dot = row_dot<VEC>(f, de);
 #pragma unroll
       for (int i = 0; i < VEC; ++i)
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
 #pragma unroll
       for (int i = 0; i < VEC; ++i) F4_OP(de[i], de[i].x * invn, de[i].y * invn, de[i].z * invn, de[i].w * invn);
     }
-    store_row<VEC>(dproj + r * d, lane, de);
+    store_row<VEC>(dproj + prow * d, lane, de);
   }
   flush_cols<VEC>(ag, dgamma, lane, warp, red);
   flush_cols<VEC>(ab, dbeta, lane, warp, red);
@@ -505,17 +506,17 @@ int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const
 int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
                      const int32_t* type_ids, const float* inv_norm, const float* mean,
                      const float* rstd, const float* pos_emb, const float* type_emb,
-                     const float* gamma, int32_t B, int32_t S, int32_t d, float p_drop,
+                     const float* gamma, int32_t B, int32_t M, int32_t T, int32_t d, float p_drop,
                      uint64_t seed, uint32_t site, float* dproj, float* dpos_emb,
                      float* dtype_emb, float* dgamma, float* dbeta, void* stream) {
   MMT_ARG_CHECK(dh && proj && pos_ids && type_ids && inv_norm && mean && rstd && pos_emb && type_emb &&
                 gamma && dproj && dpos_emb && dtype_emb && dgamma && dbeta, MMT_E_ARG, "mmt_embed_ln_bwd: null pointer");
   CHECK_D(d); CHECK_P(p_drop);
-  const int64_t rows = (int64_t)B * S;
+  const int64_t rows = (int64_t)B * (1 + M * (T + 1));
   int grid = row_grid(rows);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   DISPATCH_VEC(d, (embed_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-      dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, S, p_drop,
+      dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, M, T, p_drop,
       seed, site, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
   MMT_LAUNCH_CHECK("embed_ln_bwd");
   return 0;

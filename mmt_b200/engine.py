@@ -73,18 +73,22 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   sv = Saved()
   sv.B, sv.T, sv.S, sv.training, sv.seed = B, T, S, training, seed
   sv.p_hid, sv.p_att = p_hid, p_att
-  sv.feats, sv.maxp = feats, maxp
 
-  # ---- K1: ReduceDim GEMMs straight into the token slots (model.py:426-437, 723-726) ----
-  proj = _empty((BS, d), flat)
+  # ---- K1: ReduceDim (model.py:426-437, 723-726).  Per expert the max-pooled row and the T frame
+  # rows are packed as one [B, T+1, in] operand so the projection (and its weight gradient) is a
+  # single dense GEMM; outputs are expert-major [M, B, T+1, d] and gathered into token order by
+  # the embedding kernel.
+  R1 = B * (T + 1)
+  proj = _empty((M, R1, d), flat)
+  sv.xpack = []
   for k, mod in enumerate(cfg.mods):
     w_off = L.off("video_dim_reduce.%s.fc.weight" % mod)
     b_off = L.off("video_dim_reduce.%s.fc.bias" % mod)
     din = cfg.in_dims[k]
-    gemm(B, d, din, maxp[k], din, 1, flat, din, 1, proj, d, b_off=w_off, bias=flat,
-         bias_off=b_off, c_off=(1 + k * (T + 1)) * d, c_mb=1, c_mbs=S * d, precision=prec)
-    gemm(B * T, d, din, feats[k], din, 1, flat, din, 1, proj, d, b_off=w_off, bias=flat,
-         bias_off=b_off, c_off=(2 + k * (T + 1)) * d, c_mb=T, c_mbs=S * d, precision=prec)
+    xp = torch.cat((maxp[k].unsqueeze(1), feats[k]), 1)          # [B, T+1, in] (data movement only)
+    sv.xpack.append(xp)
+    gemm(R1, d, din, xp, din, 1, flat, din, 1, proj, d, b_off=w_off, bias=flat, bias_off=b_off,
+         c_off=k * R1 * d, precision=prec)
   sv.proj = proj
 
   # ---- K2+K3: token assembly + BertEmbeddings (model.py:485-567, bert.py:87-105) ----
@@ -178,6 +182,7 @@ def head_forward(cfg, flat, bufs, text, training, seed):
   R = text.shape[0]
   st = stream_ptr()
   lib = _lib.load()
+  prec = cfg.precision
   p_txt = cfg.p_txt if training else 0.0
   sv = Saved()
   sv.R, sv.training, sv.seed, sv.p_txt, sv.text = R, training, seed, p_txt, text
@@ -187,11 +192,11 @@ def head_forward(cfg, flat, bufs, text, training, seed):
   m0 = cfg.mods[0]
   X = _empty((R, M * d), flat)
   gemm(R, M * d, td, text, td, 1, flat, td, 1, X, M * d, b_off=L.off("text_GU.%s.fc.weight" % m0),
-       bias=flat, bias_off=L.off("text_GU.%s.fc.bias" % m0))
+       bias=flat, bias_off=L.off("text_GU.%s.fc.bias" % m0), precision=prec)
   G = _empty((R, M * d), flat)
   gemm(R, d, d, X, M * d, 1, flat, d, 1, G, M * d, b_off=L.off("text_GU.%s.cg.fc.weight" % m0),
        bias=flat, bias_off=L.off("text_GU.%s.cg.fc.bias" % m0), bias_bs=d, batch=M,
-       a_bs=(d, 0), b_bs=(d * d, 0), c_bs=(d, 0))
+       a_bs=(d, 0), b_bs=(d * d, 0), c_bs=(d, 0), precision=prec)
   txt = _empty((R, M, d), flat)
   sv.Y = _empty((R, M * d), flat)
   sv.bn_mean, sv.bn_rstd = _empty((M * d,), flat), _empty((M * d,), flat)
@@ -209,11 +214,12 @@ def head_forward(cfg, flat, bufs, text, training, seed):
     check(lib.mmt_dropout(ptr(text), ptr(tdrop), R, td, p_txt, seed, SITE_MOE_TXT, st), "mmt_dropout")
   else:
     tdrop = text
-  logits = _empty((R, M), flat)
-  gemm(R, M, td, tdrop, td, 1, flat, td, 1, logits, M, b_off=L.off("moe_fc_txt.%s.weight" % m0),
-       bias=flat, bias_off=L.off("moe_fc_txt.%s.bias" % m0))
+  Mp = (M + 3) // 4 * 4                                # logits rows padded to 16 B for the TMA path
+  logits = _empty((R, Mp), flat)
+  gemm(R, M, td, tdrop, td, 1, flat, td, 1, logits, Mp, b_off=L.off("moe_fc_txt.%s.weight" % m0),
+       bias=flat, bias_off=L.off("moe_fc_txt.%s.bias" % m0), precision=prec)
   tw = _empty((R, M), flat)
-  check(lib.mmt_moe_softmax_fwd(ptr(logits), R, M, ptr(tw), st), "mmt_moe_softmax_fwd")
+  check(lib.mmt_moe_softmax_fwd(ptr(logits), R, M, Mp, ptr(tw), st), "mmt_moe_softmax_fwd")
   sv.tdrop, sv.tw = tdrop, tw
   return txt, tw, sv
 
@@ -235,20 +241,24 @@ def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
   lib = _lib.load()
   seed = sv.seed
   m0 = cfg.mods[0]
+  prec = cfg.precision
 
   def colsum(X, rows, n, ld, out_off, rb=0, rbs=0, x_off=0):
     check(lib.mmt_colsum(ptr(X, x_off), rows, n, ld, rb, rbs, ptr(gflat, out_off), 1, st), "mmt_colsum")
 
   dtext = None
   if dtw is not None:
-    dlog = _empty((R, M), flat)
-    check(lib.mmt_moe_softmax_bwd(ptr(dtw), ptr(sv.tw), R, M, ptr(dlog), st), "mmt_moe_softmax_bwd")
+    Mp = (M + 3) // 4 * 4
+    dlog = _empty((R, Mp), flat)
+    check(lib.mmt_moe_softmax_bwd(ptr(dtw), ptr(sv.tw), R, M, Mp, ptr(dlog), st), "mmt_moe_softmax_bwd")
     # dW_moe [M, td] = dlog^T @ tdrop ; db = colsum(dlog)
-    gemm(M, td, R, dlog, 1, M, sv.tdrop, 1, td, gflat, td, c_off=L.off("moe_fc_txt.%s.weight" % m0), split_k=True)
-    colsum(dlog, R, M, M, L.off("moe_fc_txt.%s.bias" % m0))
+    gemm(M, td, R, dlog, 1, Mp, sv.tdrop, 1, td, gflat, td, c_off=L.off("moe_fc_txt.%s.weight" % m0),
+         precision=prec)
+    colsum(dlog, R, M, Mp, L.off("moe_fc_txt.%s.bias" % m0))
     if need_dtext:
       dtext = _empty((R, td), flat)
-      gemm(R, td, M, dlog, M, 1, flat, 1, td, dtext, td, b_off=L.off("moe_fc_txt.%s.weight" % m0))
+      gemm(R, td, M, dlog, Mp, 1, flat, 1, td, dtext, td, b_off=L.off("moe_fc_txt.%s.weight" % m0),
+           precision=prec)
       if sv.p_txt > 0:
         check(lib.mmt_dropout(ptr(dtext), ptr(dtext), R, td, sv.p_txt, seed, SITE_MOE_TXT, st),
               "mmt_dropout")
@@ -264,20 +274,22 @@ def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
         ptr(gflat, L.off("text_GU.%s.cg.batch_norm.bias" % m0)), st), "mmt_geu_gate_bwd")
     # cg.fc: dW2_m [d,d] = dG_m^T @ X_m ; db2 = colsum(dG) ; dX += dG_m @ W2_m
     gemm(d, d, R, dG, 1, M * d, sv.X, 1, M * d, gflat, d, c_off=L.off("text_GU.%s.cg.fc.weight" % m0),
-         batch=M, a_bs=(d, 0), b_bs=(d, 0), c_bs=(d * d, 0), split_k=True)
+         batch=M, a_bs=(d, 0), b_bs=(d, 0), c_bs=(d * d, 0), precision=prec)
     colsum(dG, R, M * d, M * d, L.off("text_GU.%s.cg.fc.bias" % m0))
     gemm(R, d, d, dG, M * d, 1, flat, 1, d, dX, M * d, b_off=L.off("text_GU.%s.cg.fc.weight" % m0),
-         add=dX, batch=M, a_bs=(d, 0), b_bs=(d * d, 0), c_bs=(d, 0))
+         add=dX, batch=M, a_bs=(d, 0), b_bs=(d * d, 0), c_bs=(d, 0), precision=prec)
     # fc: dW1 [M*d, td] = dX^T @ text ; db1 = colsum(dX) ; dtext += dX @ W1
-    gemm(M * d, td, R, dX, 1, M * d, sv.text, 1, td, gflat, td, c_off=L.off("text_GU.%s.fc.weight" % m0), split_k=True)
+    gemm(M * d, td, R, dX, 1, M * d, sv.text, 1, td, gflat, td, c_off=L.off("text_GU.%s.fc.weight" % m0),
+         precision=prec)
     colsum(dX, R, M * d, M * d, L.off("text_GU.%s.fc.bias" % m0))
     if need_dtext:
       if dtext is None:
         dtext = _empty((R, td), flat)
-        gemm(R, td, M * d, dX, M * d, 1, flat, 1, td, dtext, td, b_off=L.off("text_GU.%s.fc.weight" % m0))
+        gemm(R, td, M * d, dX, M * d, 1, flat, 1, td, dtext, td, b_off=L.off("text_GU.%s.fc.weight" % m0),
+             precision=prec)
       else:
         gemm(R, td, M * d, dX, M * d, 1, flat, 1, td, dtext, td, b_off=L.off("text_GU.%s.fc.weight" % m0),
-             add=dtext)
+             add=dtext, precision=prec)
 
   return dtext
 
@@ -370,28 +382,25 @@ def video_backward(cfg, flat, gflat, sv, dvid):
          b_off=L.off(p + "attention.self.query.weight"), add=dz1, precision=prec)
 
   # --- embeddings + token assembly backward ---
-  dproj = _empty((BS, d), flat)
+  R1 = B * (T + 1)
+  dproj = _empty((M, R1, d), flat)
   e = "vid_bert.embeddings."
   check(lib.mmt_embed_ln_bwd(
       ptr(dh_), ptr(sv.proj), ptr(sv.pos_ids), ptr(sv.type_ids), ptr(sv.inv_norm), ptr(sv.mean0),
       ptr(sv.rstd0), ptr(flat, L.off(e + "position_embeddings.weight")),
       ptr(flat, L.off(e + "token_type_embeddings.weight")), ptr(flat, L.off(e + "layer_norm.weight")),
-      B, S, d, sv.p_hid, seed, SITE_EMBED, ptr(dproj),
+      B, M, T, d, sv.p_hid, seed, SITE_EMBED, ptr(dproj),
       ptr(gflat, L.off(e + "position_embeddings.weight")),
       ptr(gflat, L.off(e + "token_type_embeddings.weight")), ptr(gflat, L.off(e + "layer_norm.weight")),
       ptr(gflat, L.off(e + "layer_norm.bias")), st), "mmt_embed_ln_bwd")
-  # --- ReduceDim weight gradients (inputs carry no gradient) ---
+  # --- ReduceDim weight gradients (inputs carry no gradient): dW [d, in] = dproj_k^T @ xpack_k ---
   for k, mod in enumerate(cfg.mods):
     w_off = L.off("video_dim_reduce.%s.fc.weight" % mod)
     b_off = L.off("video_dim_reduce.%s.fc.bias" % mod)
     din = cfg.in_dims[k]
-    base = (1 + k * (T + 1)) * d
-    # dW [d, in] = dproj[AGG rows]^T @ maxpool  +  dproj[temporal rows]^T @ features
-    gemm(d, din, B, dproj, 1, 0, sv.maxp[k], 1, din, gflat, din, a_off=base, a_kb=1, a_kbs=S * d,
-         c_off=w_off, split_k=True)
-    gemm(d, din, B * T, dproj, 1, d, sv.feats[k], 1, din, gflat, din, a_off=base + d, a_kb=T,
-         a_kbs=S * d, c_off=w_off, add=gflat, add_off=w_off)
-    colsum(dproj, B * (T + 1), d, d, b_off, rb=T + 1, rbs=S * d, x_off=base)
+    gemm(d, din, R1, dproj, 1, d, sv.xpack[k], 1, din, gflat, din, a_off=k * R1 * d, c_off=w_off,
+         precision=prec, split_k=True)
+    colsum(dproj, R1, d, d, b_off, x_off=k * R1 * d)
 
 
 def encode_forward(cfg, flat, bufs, text, feats, maxp, ft, ind, training, seed):
