@@ -16,107 +16,17 @@
 // along m / n); the latter is what the backward GEMMs (dgrad: B = W read "transposed"; wgrad:
 // A = dY^T, B = X^T) need, so no transposes are ever materialised.  The UMMA shared-memory
 // descriptors and the TMA boxes are built per layout (canonical SWIZZLE_128B atoms).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mmt {
 namespace {
+using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 8;              // tf32: 32 B of K per instruction
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 192;
-constexpr float kTf32TruncComp = 1.0f + 2.0f * 0.7213475f / 2048.0f;
-constexpr uint32_t SPIN_LIMIT = 1u << 27;   // bounded mbarrier spin: a protocol bug traps, never hangs
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (spin > SPIN_LIMIT) __trap();
-  }
-}
-// rank-4 tensor maps: {inner, rows-or-k, batch_inner, batch_outer}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
-// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms; K-major operands),
-//              1 = SWIZZLE_128B_BASE32B (32-byte swizzle atoms, 4-row period) -- the only layout the
-//                  tensor core accepts for MN-major 32-bit (tf32) operands.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address  [0,14)
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading byte offset [16,30)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride byte offset  [32,46)
-  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 struct TcArgs {
   mmt_gemm_desc d;
@@ -340,8 +250,26 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 /*align slack*/ + 128 /*barriers*/;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
+    configured = true;
+  }
+  dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k * args.d.batch);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
+  MMT_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+}  // namespace
+
 // rows x K operand, element (r, k) at base[r*rs + k*ks] with either ks == 1 (K-major) or rs == 1.
-int make_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
+int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
              int tile_rows, int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, const char* what) {
   EncodeTiledFn enc = get_encode();
   MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled unavailable");
@@ -369,23 +297,8 @@ int make_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, i
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 /*align slack*/ + 128 /*barriers*/;
-  static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
-    configured = true;
-  }
-  dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k * args.d.batch);
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
-  MMT_LAUNCH_CHECK("gemm_tc_kernel");
-  return 0;
-}
 
-}  // namespace
+int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
 
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(d.batch % d.batch_inner == 0, MMT_E_SHAPE, "gemm_tc: batch %d not a multiple of batch_inner %d",
@@ -395,6 +308,11 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(!a_mn || d.a_ms == 1, MMT_E_UNSUPPORTED, "gemm_tc: A must be contiguous along k or m");
   MMT_ARG_CHECK(!b_mn || d.b_ns == 1, MMT_E_UNSUPPORTED, "gemm_tc: B must be contiguous along k or n");
   MMT_ARG_CHECK(d.K >= 1, MMT_E_SHAPE, "gemm_tc: K=%d", d.K);
+  {
+    bool taken = false;                      // large un-batched problems: persistent 128x256 kernel
+    int prc = gemm_tc_persistent(d, stream, &taken);
+    if (prc != 0 || taken) return prc;
+  }
   constexpr int BN = 128;
   TcArgs args{d, 1, (d.K + BK - 1) / BK};
   // kind::tf32 TRUNCATES the 13 low mantissa bits of both fp32 operands (verified against a
@@ -419,9 +337,9 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   }
   CUtensorMap ma, mb;
   const int bo = d.batch / d.batch_inner;
-  int rc = make_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, bo, d.batch_inner, d.a_bs0, d.a_bs1, "A");
+  int rc = make_tf32_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, bo, d.batch_inner, d.a_bs0, d.a_bs1, "A");
   if (rc) return rc;
-  rc = make_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, bo, d.batch_inner, d.b_bs0, d.b_bs1, "B");
+  rc = make_tf32_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, bo, d.batch_inner, d.b_bs0, d.b_bs1, "B");
   if (rc) return rc;
   if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, args, stream);
   if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, args, stream);

@@ -1,0 +1,297 @@
+// Persistent tcgen05 TF32 GEMM (large un-batched problems): one CTA per SM walks a static list of
+// 128 x 256 output tiles.
+//
+//   warp 0    TMA producer     4-stage ring of {A 128x32, B 256x32} fp32 tiles (48 KB / stage)
+//   warp 1    MMA issuer       tcgen05.mma kind::tf32 M=128 N=256 K=8; the 512 TMEM columns hold TWO
+//                              accumulators so tile i+1's main loop overlaps tile i's epilogue
+//   warps 2-5 epilogue         tcgen05.ld -> per-warp shared-memory transpose -> fused
+//                              bias / residual / erf-GELU / GELU' and fully coalesced 128-bit
+//                              global loads/stores (each store instruction covers 4 complete
+//                              128-byte row segments)
+// Tiles are ordered m-fastest so the CTAs that run together share the same B (weight) tile in L2.
+// Weight-gradient shapes (few tiles, K = B*S) are split along K into (tile, k-range) work items
+// whose epilogue reduces with red.global.add.v4.f32 into a zeroed C.
+#include "tc_ptx.cuh"
+
+namespace mmt {
+namespace {
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 32, UMMA_K = 8, STAGES = 4;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STG_PITCH = 36;                         // floats; 16 B aligned rows, conflict-free v4 phases
+constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
+
+struct Tc2Args {
+  mmt_gemm_desc d;
+  int num_m_tiles, num_n_tiles;
+  int split_k, kb_per_split, num_kb;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const Tc2Args args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;       // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const mmt_gemm_desc& d = args.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = args.num_m_tiles * args.num_n_tiles;
+  const int num_work = num_tiles * args.split_k;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (m0, n0, k-block range)
+  auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+    const int tile = w / args.split_k, ks = w % args.split_k;
+    n0 = (tile / args.num_m_tiles) * BN;
+    m0 = (tile % args.num_m_tiles) * BM;
+    kb0 = ks * args.kb_per_split;
+    nkb = min(args.num_kb, kb0 + args.kb_per_split) - kb0;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t g = 0;                                  // global k-block counter (ring position)
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        decode(w, m0, n0, kb0, nkb);
+        for (int i = 0; i < nkb; ++i, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = (kb0 + i) * BK;
+          if (!A_MN) {
+            tma_load_4d(sa, &map_a, &full_bar[s], k0, m0, 0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) tma_load_4d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0, 0, 0);
+          }
+          if (!B_MN) {
+            tma_load_4d(sb, &map_b, &full_bar[s], k0, n0, 0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0, 0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = A_MN ? 512 : 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
+      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = B_MN ? 512 : 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
+      constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
+      uint32_t g = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        int m0, n0, kb0, nkb;
+        decode(w, m0, n0, kb0, nkb);
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int i = 0; i < nkb; ++i, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * A_STEP, A_LBO, A_SBO, A_LT);
+            const uint64_t db = make_smem_desc(sb + k * B_STEP, B_LBO, B_SBO, B_LT);
+            umma_tf32(acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                               // TMEM lane quarter == output rows 32q..32q+31
+    float* stg = staging + q * (32 * STG_PITCH);
+    const bool vec_ok = ((d.c_ms & 3) == 0) &&
+                        ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
+    const int sub_r = lane >> 3;                          // store phase: row within a group of 4
+    const int sub_c = (lane & 7) * 4;                     // store phase: first of this lane's 4 columns
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      const int buf = it & 1;
+      const bool lead = (kb0 == 0);
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= d.N) break;                             // warp-uniform
+        float v[32];
+        tmem_ld32(acc + (uint32_t)(c * 32), v);
+        // phase 1: this lane's row -> warp-private staging (row pitch 36 floats)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) =
+              make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha);
+        __syncwarp();
+        // phase 2: coalesced: lanes 8r..8r+7 cover one 128-byte row segment
+        const int col = nb + sub_c;
+        const bool full = vec_ok && (col + 4 <= d.N);
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (d.bias && (lead || args.split_k == 1)) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) if (col + t < d.N) bv[t] = d.bias[col + t];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub_r;
+          const int m = m0 + q * 32 + rl;
+          if (m >= d.M || col >= d.N) continue;
+          const float4 sv = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
+          float o[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
+          const int64_t off = (int64_t)m * d.c_ms + col;
+          if (d.add && (lead || args.split_k == 1)) {
+            if (full) {
+              const float4 a = *reinterpret_cast<const float4*>(d.add + off);
+              o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (col + t < d.N) o[t] += d.add[off + t];
+            }
+          }
+          if (args.split_k > 1) {
+            if (full) atomicAdd(reinterpret_cast<float4*>(d.C + off), make_float4(o[0], o[1], o[2], o[3]));
+            else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (col + t < d.N) atomicAdd(d.C + off + t, o[t]);
+            }
+            continue;
+          }
+          if (d.epilogue == MMT_EPI_GELU) {
+            if (full) *reinterpret_cast<float4*>(d.aux + off) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (col + t < d.N) d.aux[off + t] = o[t];
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = gelu_erf(o[t]);
+          } else if (d.epilogue == MMT_EPI_DGELU) {
+            float u[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full) {
+              const float4 t4 = *reinterpret_cast<const float4*>(d.aux + off);
+              u[0] = t4.x; u[1] = t4.y; u[2] = t4.z; u[3] = t4.w;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) if (col + t < d.N) u[t] = d.aux[off + t];
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] *= dgelu_erf(u[t]);
+          }
+          if (full) *reinterpret_cast<float4*>(d.C + off) = make_float4(o[0], o[1], o[2], o[3]);
+          else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (col + t < d.N) d.C[off + t] = o[t];
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);         // this warp no longer reads the accumulator
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 1024 + 128;
+  static bool configured = false;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "gemm_tc2 smem attribute");
+    configured = true;
+  }
+  const int work = args.num_m_tiles * args.num_n_tiles * args.split_k;
+  const int grid = work < num_sms() ? work : num_sms();
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
+  MMT_LAUNCH_CHECK("gemm_tc2_kernel");
+  return 0;
+}
+
+}  // namespace
+
+int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
+                  int tile_rows, int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, const char* what);
+
+// Returns 1 if the problem is not one this kernel takes (caller falls through to the tiled kernel).
+int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken) {
+  *taken = false;
+  if (d.batch != 1 || d.c_mb != 0 || d.a_kb != 0 || d.N < 192 || d.M < 256) return 0;
+  const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
+  Tc2Args args;
+  args.d = d;
+  args.d.alpha = d.alpha * kTf32TruncComp;
+  args.num_m_tiles = (d.M + BM - 1) / BM;
+  args.num_n_tiles = (d.N + BN - 1) / BN;
+  args.num_kb = (d.K + BK - 1) / BK;
+  args.split_k = 1;
+  args.kb_per_split = args.num_kb;
+  const int tiles = args.num_m_tiles * args.num_n_tiles;
+  if ((d.flags & MMT_GEMM_SPLIT_K) && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE && d.add != d.C &&
+      tiles * 2 <= num_sms() && args.num_kb >= 32) {
+    int split = num_sms() / tiles;
+    if (split > args.num_kb / 8) split = args.num_kb / 8;
+    if (split > 1) {
+      args.kb_per_split = (args.num_kb + split - 1) / split;
+      args.split_k = (args.num_kb + args.kb_per_split - 1) / args.kb_per_split;
+      cudaError_t e = cudaMemsetAsync(d.C, 0, sizeof(float) * (size_t)d.M * d.N, stream);
+      if (e != cudaSuccess) return cuda_status(e, "gemm_tc2 split-K memset");
+    }
+  }
+  CUtensorMap ma, mb;
+  int rc = make_tf32_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, 1, 1, 0, 0, "A");
+  if (rc) return rc;
+  rc = make_tf32_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, 1, 1, 0, 0, "B");
+  if (rc) return rc;
+  *taken = true;
+  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, args, stream);
+  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, args, stream);
+  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, args, stream);
+  return launch2<true, true>(ma, mb, args, stream);
+}
+
+}  // namespace mmt
