@@ -90,4 +90,30 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
+// Branch-free erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7), one MUFU.EX2 + one MUFU.RCP.
+// The tensor-core epilogues use it: with only four epilogue warps per SM the long dependent chain
+// (and the divergent range split) of libdevice's erff made GELU the bottleneck of the FFN GEMMs.
+// e = exp(-u^2/2) is shared between erf(u/sqrt2) and the Gaussian pdf needed by GELU'.
+__device__ __forceinline__ void erf_parts(float u, float& erf_v, float& e) {
+  const float x = u * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  e = exp2f(-ax * ax * 1.44269504088896340736f);
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  erf_v = copysignf(fmaf(-p * t, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float u) {
+  float er, e;
+  erf_parts(u, er, e);
+  return 0.5f * u * (1.0f + er);
+}
+__device__ __forceinline__ float dgelu_fast(float u) {
+  float er, e;
+  erf_parts(u, er, e);
+  return fmaf(u * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
+}
+
 }  // namespace mmt

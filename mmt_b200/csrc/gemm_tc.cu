@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
             for (int q = 0; q < 4; ++q) if (ok[q]) auxrow[j + q] = o[q];
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[q] = gelu_erf(o[q]);
+          for (int q = 0; q < 4; ++q) o[q] = gelu_fast(o[q]);
         } else if (d.epilogue == MMT_EPI_DGELU) {
           float u[4] = {0.f, 0.f, 0.f, 0.f};
           if (full) {
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
             for (int q = 0; q < 4; ++q) if (ok[q]) u[q] = auxrow[j + q];
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[q] *= dgelu_erf(u[q]);
+          for (int q = 0; q < 4; ++q) o[q] *= dgelu_fast(u[q]);
         }
         if (full) *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
         else {

@@ -170,55 +170,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
 #pragma unroll
           for (int t = 0; t < 4; ++t) if (col + t < d.N) bv[t] = d.bias[col + t];
         }
+        // (a) gather this lane's 8 row-segments (registers), (b) one batch of independent loads,
+        // (c) math on 32 independent values (ILP hides the ALU/MUFU latency that four epilogue
+        // warps per SM cannot hide with thread-level parallelism), (d) stores.
+        float4 o[8];
+        bool ok[8];
+        int64_t off[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + sub_r;
           const int m = m0 + q * 32 + rl;
-          if (m >= d.M || col >= d.N) continue;
-          const float4 sv = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
-          float o[4] = {sv.x + bv[0], sv.y + bv[1], sv.z + bv[2], sv.w + bv[3]};
-          const int64_t off = (int64_t)m * d.c_ms + col;
+          ok[i] = (m < d.M) && (col < d.N);
+          off[i] = (int64_t)m * d.c_ms + col;
+          o[i] = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
+          o[i].x += bv[0]; o[i].y += bv[1]; o[i].z += bv[2]; o[i].w += bv[3];
+        }
+        if (full) {
           if (d.add && (lead || args.split_k == 1)) {
-            if (full) {
-              const float4 a = *reinterpret_cast<const float4*>(d.add + off);
-              o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
-            } else {
+            float4 a[8];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) if (col + t < d.N) o[t] += d.add[off + t];
-            }
+            for (int i = 0; i < 8; ++i) a[i] = ok[i] ? *reinterpret_cast<const float4*>(d.add + off[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o[i].x += a[i].x; o[i].y += a[i].y; o[i].z += a[i].z; o[i].w += a[i].w; }
           }
           if (args.split_k > 1) {
-            if (full) atomicAdd(reinterpret_cast<float4*>(d.C + off), make_float4(o[0], o[1], o[2], o[3]));
-            else {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) if (col + t < d.N) atomicAdd(d.C + off + t, o[t]);
+            for (int i = 0; i < 8; ++i) if (ok[i]) atomicAdd(reinterpret_cast<float4*>(d.C + off[i]), o[i]);
+          } else {
+            if (d.epilogue == MMT_EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) if (ok[i]) *reinterpret_cast<float4*>(d.aux + off[i]) = o[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = make_float4(gelu_fast(o[i].x), gelu_fast(o[i].y), gelu_fast(o[i].z), gelu_fast(o[i].w));
+            } else if (d.epilogue == MMT_EPI_DGELU) {
+              float4 u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = ok[i] ? *reinterpret_cast<const float4*>(d.aux + off[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                o[i].x *= dgelu_fast(u[i].x); o[i].y *= dgelu_fast(u[i].y);
+                o[i].z *= dgelu_fast(u[i].z); o[i].w *= dgelu_fast(u[i].w);
+              }
             }
-            continue;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (ok[i]) *reinterpret_cast<float4*>(d.C + off[i]) = o[i];
           }
-          if (d.epilogue == MMT_EPI_GELU) {
-            if (full) *reinterpret_cast<float4*>(d.aux + off) = make_float4(o[0], o[1], o[2], o[3]);
-            else {
+        } else {
+          // ragged right edge / unaligned C: predicated scalars
 #pragma unroll
-              for (int t = 0; t < 4; ++t) if (col + t < d.N) d.aux[off + t] = o[t];
+          for (int i = 0; i < 8; ++i) {
+            if (!ok[i]) continue;
+            float ov[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (col + t >= d.N) continue;
+              float val = ov[t];
+              if (d.add && (lead || args.split_k == 1)) val += d.add[off[i] + t];
+              if (args.split_k > 1) { atomicAdd(d.C + off[i] + t, val); continue; }
+              if (d.epilogue == MMT_EPI_GELU) { d.aux[off[i] + t] = val; val = gelu_fast(val); }
+              else if (d.epilogue == MMT_EPI_DGELU) val *= dgelu_fast(d.aux[off[i] + t]);
+              d.C[off[i] + t] = val;
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) o[t] = gelu_erf(o[t]);
-          } else if (d.epilogue == MMT_EPI_DGELU) {
-            float u[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full) {
-              const float4 t4 = *reinterpret_cast<const float4*>(d.aux + off);
-              u[0] = t4.x; u[1] = t4.y; u[2] = t4.z; u[3] = t4.w;
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) if (col + t < d.N) u[t] = d.aux[off + t];
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) o[t] *= dgelu_erf(u[t]);
-          }
-          if (full) *reinterpret_cast<float4*>(d.C + off) = make_float4(o[0], o[1], o[2], o[3]);
-          else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (col + t < d.N) d.C[off + t] = o[t];
           }
         }
         __syncwarp();
