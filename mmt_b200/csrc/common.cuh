@@ -94,11 +94,21 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 // The tensor-core epilogues use it: with only four epilogue warps per SM the long dependent chain
 // (and the divergent range split) of libdevice's erff made GELU the bottleneck of the FFN GEMMs.
 // e = exp(-u^2/2) is shared between erf(u/sqrt2) and the Gaussian pdf needed by GELU'.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // one MUFU.RCP, 1 ulp; no slow-path call
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // one MUFU.EX2, 2 ulp
+  return r;
+}
 __device__ __forceinline__ void erf_parts(float u, float& erf_v, float& e) {
   const float x = u * 0.70710678118654752440f;
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  e = exp2f(-ax * ax * 1.44269504088896340736f);
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
+  e = fast_ex2(-ax * ax * 1.44269504088896340736f);
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);

@@ -17,9 +17,9 @@ namespace mmt {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BK = 32, UMMA_K = 8, STAGES = 4;
+constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int NUM_THREADS = 192;
-constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr int STG_PITCH = 36;                         // floats; 16 B aligned rows, conflict-free v4 phases
 constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
 
@@ -29,10 +29,13 @@ struct Tc2Args {
   int split_k, kb_per_split, num_kb;
 };
 
-template <bool A_MN, bool B_MN>
+// BN = 256: 4-stage ring of 48 KB; BN = 128 (narrow / batched attention problems): 6 stages of 32 KB.
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const Tc2Args args) {
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  constexpr uint32_t B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
   const mmt_gemm_desc& d = args.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = args.num_m_tiles * args.num_n_tiles;
-  const int num_work = num_tiles * args.split_k;
+  const int num_work = num_tiles * args.split_k * d.batch;      // split-K and batching are exclusive
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -54,14 +57,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item -> (m0, n0, k-block range)
-  auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+  // work item -> (batch z, m0, n0, k-block range)
+  auto decode = [&](int w, int& z, int& m0, int& n0, int& kb0, int& nkb) {
+    z = w / (num_tiles * args.split_k);
+    w -= z * num_tiles * args.split_k;
     const int tile = w / args.split_k, ks = w % args.split_k;
     n0 = (tile / args.num_m_tiles) * BN;
     m0 = (tile % args.num_m_tiles) * BM;
@@ -74,8 +79,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
     if (lane == 0) {
       uint32_t g = 0;                                  // global k-block counter (ring position)
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        int m0, n0, kb0, nkb;
-        decode(w, m0, n0, kb0, nkb);
+        int z, m0, n0, kb0, nkb;
+        decode(w, z, m0, n0, kb0, nkb);
+        const int z0 = z / d.batch_inner, z1 = z % d.batch_inner;
         for (int i = 0; i < nkb; ++i, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1;
@@ -85,16 +91,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
           uint8_t* sb = sa + A_BYTES;
           const int k0 = (kb0 + i) * BK;
           if (!A_MN) {
-            tma_load_4d(sa, &map_a, &full_bar[s], k0, m0, 0, 0);
+            tma_load_4d(sa, &map_a, &full_bar[s], k0, m0, z1, z0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_4d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0, 0, 0);
+            for (int j = 0; j < BM / 32; ++j) tma_load_4d(sa + j * (BK * 128), &map_a, &full_bar[s], m0 + 32 * j, k0, z1, z0);
           }
           if (!B_MN) {
-            tma_load_4d(sb, &map_b, &full_bar[s], k0, n0, 0, 0);
+            tma_load_4d(sb, &map_b, &full_bar[s], k0, n0, z1, z0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0, 0, 0);
+            for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0, z1, z0);
           }
         }
       }
@@ -109,8 +115,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
       uint32_t g = 0;
       int it = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        int m0, n0, kb0, nkb;
-        decode(w, m0, n0, kb0, nkb);
+        int z, m0, n0, kb0, nkb;
+        decode(w, z, m0, n0, kb0, nkb);
         const int buf = it & 1;
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
         tc_fence_after();
@@ -137,16 +143,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                               // TMEM lane quarter == output rows 32q..32q+31
     float* stg = staging + q * (32 * STG_PITCH);
-    const bool vec_ok = ((d.c_ms & 3) == 0) &&
+    const bool vec_ok = ((d.c_ms & 3) == 0) && (((d.c_bs0 | d.c_bs1 | d.bias_bs) & 3) == 0) &&
                         ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
     const int sub_r = lane >> 3;                          // store phase: row within a group of 4
     const int sub_c = (lane & 7) * 4;                     // store phase: first of this lane's 4 columns
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      int m0, n0, kb0, nkb;
-      decode(w, m0, n0, kb0, nkb);
+      int z, m0, n0, kb0, nkb;
+      decode(w, z, m0, n0, kb0, nkb);
       const int buf = it & 1;
       const bool lead = (kb0 == 0);
+      const int64_t zoff = (int64_t)(z / d.batch_inner) * d.c_bs0 + (int64_t)(z % d.batch_inner) * d.c_bs1;
+      const float* bias = d.bias ? d.bias + (int64_t)z * d.bias_bs : nullptr;
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
@@ -166,9 +174,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
         const int col = nb + sub_c;
         const bool full = vec_ok && (col + 4 <= d.N);
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (d.bias && (lead || args.split_k == 1)) {
+        if (bias && (lead || args.split_k == 1)) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) if (col + t < d.N) bv[t] = d.bias[col + t];
+          for (int t = 0; t < 4; ++t) if (col + t < d.N) bv[t] = bias[col + t];
         }
         // (a) gather this lane's 8 row-segments (registers), (b) one batch of independent loads,
         // (c) math on 32 independent values (ILP hides the ALU/MUFU latency that four epilogue
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
           const int rl = 4 * i + sub_r;
           const int m = m0 + q * 32 + rl;
           ok[i] = (m < d.M) && (col < d.N);
-          off[i] = (int64_t)m * d.c_ms + col;
+          off[i] = zoff + (int64_t)m * d.c_ms + col;
           o[i] = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
           o[i].x += bv[0]; o[i].y += bv[1]; o[i].z += bv[2]; o[i].w += bv[3];
         }
@@ -247,17 +255,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 1024 + 128;
+  constexpr int STAGES = BN == 256 ? 4 : 6;
+  constexpr size_t smem = STAGES * (A_BYTES + BN * BK * 4) + 4 * STG_BYTES_PER_WARP + 1024 + 128;
   static bool configured = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  auto kern = gemm_tc2_kernel<BN, A_MN, B_MN>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc2 smem attribute");
     configured = true;
   }
-  const int work = args.num_m_tiles * args.num_n_tiles * args.split_k;
+  const int work = args.num_m_tiles * args.num_n_tiles * args.split_k * args.d.batch;
   const int grid = work < num_sms() ? work : num_sms();
   kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
   MMT_LAUNCH_CHECK("gemm_tc2_kernel");
@@ -269,22 +278,42 @@ int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, c
 int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t rs, int64_t ks, bool mn_major,
                   int tile_rows, int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, const char* what);
 
-// Returns 1 if the problem is not one this kernel takes (caller falls through to the tiled kernel).
+namespace {
+template <int BN>
+int dispatch2(const mmt_gemm_desc& d, Tc2Args& args, bool a_mn, bool b_mn, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  const int bo = d.batch / d.batch_inner;
+  int rc = make_tf32_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, bo, d.batch_inner, d.a_bs0, d.a_bs1, "A");
+  if (rc) return rc;
+  rc = make_tf32_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, bo, d.batch_inner, d.b_bs0, d.b_bs1, "B");
+  if (rc) return rc;
+  args.num_n_tiles = (d.N + BN - 1) / BN;
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ma, mb, args, stream);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ma, mb, args, stream);
+  if (a_mn && !b_mn) return launch2<BN, true, false>(ma, mb, args, stream);
+  return launch2<BN, true, true>(ma, mb, args, stream);
+}
+}  // namespace
+
+// Sets *taken when this kernel handled the problem (else the caller uses the tiled kernel).
 int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken) {
   *taken = false;
-  if (d.batch != 1 || d.c_mb != 0 || d.a_kb != 0 || d.N < 192 || d.M < 256) return 0;
+  if (d.c_mb != 0 || d.a_kb != 0 || d.batch % d.batch_inner != 0) return 0;
+  const int64_t work128 = (int64_t)((d.M + BM - 1) / BM) * ((d.N + 127) / 128) * d.batch;
+  if (d.M < 128 || work128 < 96) return 0;                  // tiny problems: tiled kernel
   const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
+  const bool wide = d.N > 160;                               // 128 x 256 tiles unless N is narrow
   Tc2Args args;
   args.d = d;
   args.d.alpha = d.alpha * kTf32TruncComp;
   args.num_m_tiles = (d.M + BM - 1) / BM;
-  args.num_n_tiles = (d.N + BN - 1) / BN;
+  args.num_n_tiles = (d.N + (wide ? 255 : 127)) / (wide ? 256 : 128);
   args.num_kb = (d.K + BK - 1) / BK;
   args.split_k = 1;
   args.kb_per_split = args.num_kb;
   const int tiles = args.num_m_tiles * args.num_n_tiles;
-  if ((d.flags & MMT_GEMM_SPLIT_K) && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE && d.add != d.C &&
-      tiles * 2 <= num_sms() && args.num_kb >= 32) {
+  if ((d.flags & MMT_GEMM_SPLIT_K) && d.batch == 1 && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&
+      d.add != d.C && tiles * 2 <= num_sms() && args.num_kb >= 32) {
     int split = num_sms() / tiles;
     if (split > args.num_kb / 8) split = args.num_kb / 8;
     if (split > 1) {
@@ -294,16 +323,8 @@ int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken)
       if (e != cudaSuccess) return cuda_status(e, "gemm_tc2 split-K memset");
     }
   }
-  CUtensorMap ma, mb;
-  int rc = make_tf32_map(&ma, d.A, d.M, d.K, d.a_ms, d.a_ks, a_mn, BM, 1, 1, 0, 0, "A");
-  if (rc) return rc;
-  rc = make_tf32_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, 1, 1, 0, 0, "B");
-  if (rc) return rc;
   *taken = true;
-  if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, args, stream);
-  if (!a_mn && b_mn) return launch2<false, true>(ma, mb, args, stream);
-  if (a_mn && !b_mn) return launch2<true, false>(ma, mb, args, stream);
-  return launch2<true, true>(ma, mb, args, stream);
+  return wide ? dispatch2<256>(d, args, a_mn, b_mn, stream) : dispatch2<128>(d, args, a_mn, b_mn, stream);
 }
 
 }  // namespace mmt
