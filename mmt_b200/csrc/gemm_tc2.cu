@@ -251,14 +251,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
 template <int BN, bool A_MN, bool B_MN>
 int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, cudaStream_t stream) {
   constexpr int STAGES = BN == 256 ? 4 : 6;
-  constexpr size_t smem = STAGES * (A_BYTES + BN * BK * 4) + 4 * STG_BYTES_PER_WARP + 1024 + 128;
+  constexpr size_t smem = STAGES * (A_BYTES + BN * BK * 4) + 4 * STG_BYTES_PER_WARP + 1024 + 256;
   static bool configured = false;
   auto kern = gemm_tc2_kernel<BN, A_MN, B_MN>;
   if (!configured) {

@@ -496,12 +496,14 @@ def test_gemm_tf32_epilogues_and_splitk(dev):
   assert H.rel_err(dW2, TF32_COMP * (_tf32_trunc(dY).double().t() @ _tf32_trunc(X[:, :512]).double())) < 1e-4
 
 
-def test_gemm_tf32_batched_attention_layouts(dev):
+@pytest.mark.parametrize("Bt", [3, 40])
+def test_gemm_tf32_batched_attention_layouts(dev, Bt):
   """The six attention matmuls (scores, context and their four backward products) as batched
-  tcgen05 GEMMs over (b, h) with head-strided operands (rank-4 TMA maps)."""
+  tcgen05 GEMMs over (b, h) with head-strided operands (rank-4 TMA maps).  Bt=3 takes the tiled
+  kernel, Bt=40 the persistent one (work items = (b, h, tile))."""
   from mmt_b200 import _lib
   g = torch.Generator().manual_seed(33)
-  Bt, Hh, S, dh = 3, 4, 218, 128
+  Hh, S, dh = 4, 218, 128
   d = Hh * dh
   Sp = (S + 3) // 4 * 4
   qkv = torch.randn(Bt * S, 3 * d, generator=g).to(dev)
