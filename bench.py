@@ -190,8 +190,7 @@ def run_b200(args):
                                "attention_probs_dropout_prob": DROPOUT}, txt_bert=feed)
   net.load_state_dict(P, strict=True)
   net.to(dev).train()
-  if args.precision == "tf32":
-    net.cfg.precision = _lib.PREC_TF32
+  net.cfg.precision = _lib.PREC_TF32 if args.precision == "tf32" else _lib.PREC_FP32
   if world > 1:
     net.enable_data_parallel()
   crit = MaxMarginRankingLoss(margin=0.05, fix_norm=True)
@@ -488,7 +487,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-  ap.add_argument("--precision", default=os.environ.get("MMT_PRECISION", "fp32"),
+  ap.add_argument("--precision", default=os.environ.get("MMT_PRECISION", "tf32"),
                   choices=["fp32", "tf32"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-hbm-probe", action="store_true")

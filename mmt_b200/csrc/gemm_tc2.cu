@@ -300,7 +300,8 @@ int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken)
   *taken = false;
   if (d.c_mb != 0 || d.a_kb != 0 || d.batch % d.batch_inner != 0) return 0;
   const int64_t work128 = (int64_t)((d.M + BM - 1) / BM) * ((d.N + 127) / 128) * d.batch;
-  if (d.M < 128 || work128 < 96) return 0;                  // tiny problems: tiled kernel
+  const bool splittable = (d.flags & MMT_GEMM_SPLIT_K) && d.batch == 1 && d.K >= 1024;
+  if (d.M < 128 || (work128 < 96 && !splittable)) return 0;  // tiny problems: tiled kernel
   const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
   const bool wide = d.N > 160;                               // 128 x 256 tiles unless N is narrow
   Tc2Args args;

@@ -38,7 +38,10 @@ class Config:
     self.p_txt = float(txt_dropout)
     self.type_idx = type_idx            # list of int per expert (sorted order)
     self.in_dims = [layout.expert_dims[m]["dim"] for m in layout.mods]
-    self.precision = PREC_FP32          # linear layers: PREC_TF32 = tcgen05 tensor-core path
+    # PREC_TF32 (default): every linear layer and the attention matmuls run on the tcgen05
+    # tensor-core kernels (tf32 operands, fp32 accumulate; outputs within 1e-3 of the fp32
+    # reference, tests/test_gpu_parity.py).  PREC_FP32: CUDA-core fp32 FMAs everywhere (~1e-6).
+    self.precision = PREC_TF32
     self.attn_precision = None          # attention matmuls; None -> same as `precision`
 
 

@@ -39,7 +39,8 @@ def make_case(modalities, B, T, layers=4, dropout=0.0, caps=1, seed=1234, dense=
   return ed, vb, P, batch, cfg
 
 
-def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda"):
+def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda", precision="fp32"):
+  from mmt_b200 import _lib
   from mmt_b200.model.model import CENet
   W = batch["token_ids"].shape[2]
   R = batch["text_feat"].shape[0]
@@ -53,6 +54,7 @@ def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda"):
                                "attention_probs_dropout_prob": dropout},
               txt_bert=TxtStub(hidden.to(device)))
   net.load_state_dict(P, strict=True)
+  net.cfg.precision = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
   return net.to(device)
 
 
