@@ -242,6 +242,8 @@ def test_max_margin_sizes(dev, n):
   ref.backward()
   assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
   assert H.rel_err(dx, xr.grad) < 1e-5
+  loss_f, none = engine.max_margin(x.to(dev), 0.05, True, want_grad=False)   # streaming forward-only kernel
+  assert none is None and abs(float(loss_f) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
 
 
 def test_sims_backward_matches_oracle_autograd(dev):
