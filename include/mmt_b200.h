@@ -146,6 +146,18 @@ int mmt_softmax_mask_bwd(float* dP_inout, const float* Psoft, int32_t B, int32_t
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused flash-style self-attention forward (model/bert.py:136-172) on tcgen05 tensor cores:
+ *   ctx[b,i,h*dh:(h+1)*dh] = dropout(softmax(Q K^T * scale + (1 - mask[b,:]) * -10000)) V
+ * qkv [B*S, 3*H*dh] holds Q | K | V column blocks (the fused QKV projection's output); scores and
+ * probabilities stay in TMEM -- nothing of size S x S touches HBM.  lse [B,H,S] (may be NULL)
+ * receives the log-sum-exp of the masked, scaled scores.  dh must be 128.  The dropout mask is
+ * the same function of (seed, site, (b*H+h)*S+i, j/4) that mmt_softmax_mask_fwd uses.
+ * ------------------------------------------------------------------------------------------- */
+int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B, int32_t H, int32_t S,
+                      int32_t dh, float scale, float p_drop, uint64_t seed, uint32_t site,
+                      float* ctx, float* lse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Expert read-out + L2 normalisation (model/model.py:583-587, 621-623):
  * v[b,k,:] = normalize(h[b, 1 + k*(T+1), :]).  Backward scatters into dh (other rows zeroed).
  * ------------------------------------------------------------------------------------------- */

@@ -1,0 +1,313 @@
+// Fused flash-style self-attention forward on tcgen05 (model/bert.py:136-172, one kernel):
+//     ctx[b, i, h*dh:(h+1)*dh] = dropout(softmax(Q K^T / sqrt(dh) + (1 - mask) * -10000)) V
+// The S x S score / probability matrices are NEVER written to HBM: S = Q K^T is accumulated in
+// TMEM, the softmax warps turn it into P in place (tcgen05.ld -> registers -> tcgen05.st), and
+// P is consumed as the A operand of the second tensor-core product straight from TMEM.
+//
+// One CTA per (b, h, 128-query tile); keys are processed in blocks of KB = 224 (S = 218 fits one
+// block; longer sequences take several with an online-softmax rescale of the TMEM accumulator).
+//   warp 0    TMA producer: Q tile [128 x dh] (K-major, 4 swizzle-128B sub-tiles), then per key block
+//             K [KB x dh] (K-major) and -- once the score MMAs have drained K -- V [KB x dh] into
+//             the SAME buffer as an MN-major operand (swizzle-128B/32B-atom boxes)
+//   warp 1    MMA issuer: S = Q K^T (kind::tf32, M=128, N=KB, 16 k-steps, operands in smem), then
+//             O += P V (A = P from TMEM, B = V from smem, KB/8 k-steps)
+//   warps 2-5 softmax: one thread per query row; scale + additive mask, running max / sum, exp2,
+//             Philox dropout (identical keying to the unfused path), write P, rescale O if the
+//             running max moved; finally O / l -> ctx and log-sum-exp for the backward pass
+// Shared memory: Q 64 KB + K|V 112 KB = 176 KB; TMEM: S/P 224 columns + O 128 columns.
+#include "tc_ptx.cuh"
+
+namespace mmt {
+namespace {
+using namespace tc;
+
+constexpr int DH = 128;                 // head dim (4 sub-tiles of 32 fp32 = 128 B rows)
+constexpr int QM = 128;                 // query rows per CTA
+constexpr int KB = 224;                 // keys per block (UMMA N, multiple of 16, <= 256)
+constexpr int ATT_THREADS = 192;
+constexpr uint32_t Q_BYTES = QM * DH * 4;          // 64 KB
+constexpr uint32_t KV_BYTES = KB * DH * 4;         // 112 KB
+constexpr uint32_t TM_S = 0, TM_O = 256;           // TMEM column offsets (512 allocated)
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
+        "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
+        "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct AttArgs {
+  const float* mask;      // [B, S] 1 = attend
+  float* ctx;             // [B*S, H*DH]
+  float* lse;             // [B, H, S] natural-log sum-exp of the masked, scaled scores
+  int B, H, S;
+  float scale_log2;       // (1/sqrt(dh)) * tf32 compensation * log2(e)
+  float mask_log2;        // -10000 * log2(e)
+  float out_scale;        // tf32 compensation of the P V product
+  float p_drop, inv_keep;
+  uint64_t seed;
+  uint32_t site;
+};
+
+// map_qk: qkv viewed as [B*S rows, 3*H*DH cols], box {32 cols, rows<=256}, SWIZZLE_128B
+// map_v : same tensor, box {32 cols, 32 rows}, SWIZZLE_128B_ATOM_32B (MN-major B operand)
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                       const __grid_constant__ CUtensorMap map_k,
+                                                                       const __grid_constant__ CUtensorMap map_v,
+                                                                       const AttArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sq = smem;                       // 4 sub-tiles [128 rows x 128 B]
+  uint8_t* skv = smem + Q_BYTES;            // K: 4 sub-tiles [224 rows x 128 B];  V: 4 n-chunks [224 k-rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + KV_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* k_free = bars + 3;              // score MMAs have finished reading K
+  uint64_t* v_free = bars + 4;              // P V MMAs have finished reading V
+  uint64_t* s_full = bars + 5;              // scores ready in TMEM
+  uint64_t* p_full = bars + 6;              // probabilities written (and O rescaled) -- 128 arrivals
+  uint64_t* o_full = bars + 7;              // P V accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* smask = reinterpret_cast<float*>(bars + 16);      // additive mask of the current key block (log2 domain)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, S = args.S;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * QM;
+  const int nblk = (S + KB - 1) / KB;
+  const int d_model = H * DH;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], i == 6 ? 128 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int row_q = b * S + q0;
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) tma_load_2d(sq + t * (QM * 128), &map_q, q_full, h * DH + 32 * t, row_q);
+      for (int j = 0; j < nblk; ++j) {
+        const int row_k = b * S + j * KB;
+        mbar_wait(v_free, (j & 1) ^ 1);                       // previous block's V no longer read
+        mbar_arrive_expect_tx(k_full, KV_BYTES);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          tma_load_2d(skv + t * (KB * 128), &map_k, k_full, d_model + h * DH + 32 * t, row_k);
+        mbar_wait(k_free, j & 1);                             // scores done: K's buffer can take V
+        mbar_arrive_expect_tx(v_full, KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)                            // n-chunk c: dh columns 32c..32c+31
+#pragma unroll
+          for (int kb = 0; kb < KB / 32; ++kb)
+            tma_load_2d(skv + c * (KB * 128) + kb * (32 * 128), &map_v, v_full, 2 * d_model + h * DH + 32 * c,
+                        row_k + 32 * kb);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_tf32(QM, KB, false, false);     // S[128 x KB] = Q K^T
+      const uint32_t idesc_o = make_idesc_tf32(QM, DH, false, true);      // O[128 x dh] += P V (V MN-major)
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(k_full, j & 1);
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);            // S/P columns are free again
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DH / 8; ++ks) {
+          const uint64_t da = make_smem_desc(smem_u32(sq) + (ks >> 2) * (QM * 128) + (ks & 3) * 32, 16, 1024, 2);
+          const uint64_t db = make_smem_desc(smem_u32(skv) + (ks >> 2) * (KB * 128) + (ks & 3) * 32, 16, 1024, 2);
+          umma_tf32(tmem + TM_S, da, db, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(k_free);
+        umma_commit(s_full);
+        mbar_wait(v_full, j & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        for (int ks = 0; ks < KB / 8; ++ks) {
+          // V: n-chunks KB*128 B apart (LBO), 4-row k-groups 512 B apart (SBO), 8 keys per step = 1024 B
+          const uint64_t db = make_smem_desc(smem_u32(skv) + ks * 1024, KB * 128, 512, 1);
+          umma_tf32_ts(tmem + TM_O, tmem + TM_S + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(v_free);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                               // query row within the tile == TMEM lane
+    const int qi = q0 + r;
+    const bool row_ok = qi < S;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float* mrow = args.mask + (int64_t)b * S;
+    const uint32_t prow = (uint32_t)(((int64_t)b * H + h) * S + qi);   // Philox row id (== unfused path)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * KB;
+      // additive mask terms of this key block, shared by the 128 softmax threads (named barrier 1)
+      for (int t = threadIdx.x - 64; t < KB; t += 128) {
+        const int key = key0 + t;
+        smask[t] = key < S ? (1.0f - __ldg(mrow + key)) * args.mask_log2 : -INFINITY;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: block max of the masked, scaled scores (log2 domain)
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KB / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) m_blk = fmaxf(m_blk, fmaf(v[t], args.scale_log2, smask[c * 32 + t]));
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = (j == 0) ? 0.f : fast_ex2(m_run - m_new);
+      // pass 2: p = 2^(x - m_new), row sum (un-dropped), dropout, write P in place of S
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KB / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+#pragma unroll
+        for (int t4 = 0; t4 < 32; t4 += 4) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (args.p_drop > 0.f)
+            sc = dropout_scale4(args.seed, args.site, prow, (uint32_t)((key0 + c * 32 + t4) >> 2), args.p_drop,
+                                args.inv_keep);
+          const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int t = t4 + u;
+            const float p = fast_ex2(fmaf(v[t], args.scale_log2, smask[c * 32 + t]) - m_new);   // 2^-inf = 0 past S
+            l_blk += p;
+            v[t] = p * scv[u];
+          }
+        }
+        tmem_st32(tmem + TM_S + lane_addr + c * 32, v);
+      }
+      // online-softmax rescale of the running accumulator (only when there was a previous block)
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);                        // previous P V has landed in O
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < DH / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem + TM_O + lane_addr + c * 32, v);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] *= alpha;
+          tmem_st32(tmem + TM_O + lane_addr + c * 32, v);
+        }
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(p_full);
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // smask is rewritten by the next block
+    }
+    // epilogue: O / l -> ctx, log-sum-exp for backward
+    mbar_wait(o_full, (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv_l = args.out_scale / l_run;
+    float* orow = args.ctx + ((int64_t)b * S + qi) * d_model + h * DH;
+#pragma unroll 1
+    for (int c = 0; c < DH / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem + TM_O + lane_addr + c * 32, v);
+      if (row_ok) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 4)
+          *reinterpret_cast<float4*>(orow + c * 32 + t) =
+              make_float4(v[t] * inv_l, v[t + 1] * inv_l, v[t + 2] * inv_l, v[t + 3] * inv_l);
+      }
+    }
+    if (row_ok && args.lse)
+      args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_run)) * 0.69314718055994530942f;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows, bool atom32, const char* what);
+
+}  // namespace mmt
+
+using namespace mmt;
+
+extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B, int32_t H, int32_t S,
+                                 int32_t dh, float scale, float p_drop, uint64_t seed, uint32_t site,
+                                 float* ctx, float* lse, void* stream) {
+  MMT_ARG_CHECK(qkv && mask && ctx, MMT_E_ARG, "mmt_attention_fwd: null pointer");
+  MMT_ARG_CHECK(dh == DH, MMT_E_SHAPE, "mmt_attention_fwd: head dim %d unsupported (only %d)", dh, DH);
+  MMT_ARG_CHECK(B > 0 && H > 0 && S > 0 && B <= 65535 && H <= 65535, MMT_E_SHAPE, "mmt_attention_fwd: bad shape B=%d H=%d S=%d", B, H, S);
+  MMT_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f, MMT_E_ARG, "mmt_attention_fwd: p_drop=%f", (double)p_drop);
+  const int64_t rows = (int64_t)B * S, cols = 3LL * H * DH;
+  CUtensorMap mq, mk, mv;
+  int rc = make_tf32_map2d(&mq, qkv, rows, cols, cols, 32, QM, false, "Q");
+  if (rc) return rc;
+  rc = make_tf32_map2d(&mk, qkv, rows, cols, cols, 32, KB, false, "K");
+  if (rc) return rc;
+  rc = make_tf32_map2d(&mv, qkv, rows, cols, cols, 32, 32, true, "V");
+  if (rc) return rc;
+  AttArgs a;
+  a.mask = mask; a.ctx = ctx; a.lse = lse;
+  a.B = B; a.H = H; a.S = S;
+  a.scale_log2 = scale * tc::kTf32TruncComp * 1.44269504088896340736f;
+  a.mask_log2 = -10000.0f * 1.44269504088896340736f;
+  a.out_scale = tc::kTf32TruncComp;
+  a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  a.seed = seed; a.site = site;
+  constexpr size_t smem = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "attention_fwd smem attribute");
+    configured = true;
+  }
+  dim3 grid((S + QM - 1) / QM, H, B);
+  attention_fwd_kernel<<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(mq, mk, mv, a);
+  MMT_LAUNCH_CHECK("attention_fwd_kernel");
+  return 0;
+}

@@ -298,6 +298,24 @@ int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t 
 }
 
 
+// Plain 2-D fp32 tensor map [rows, cols] (row pitch ld floats), box {box_cols, box_rows}.
+int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows, bool atom32, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0, MMT_E_ALIGN,
+                "tensor map %s needs a 16-byte aligned base and row pitch", what);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
 int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
 
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {

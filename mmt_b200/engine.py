@@ -43,6 +43,9 @@ class Config:
     # reference, tests/test_gpu_parity.py).  PREC_FP32: CUDA-core fp32 FMAs everywhere (~1e-6).
     self.precision = PREC_TF32
     self.attn_precision = None          # attention matmuls; None -> same as `precision`
+    # flash-style fused attention forward (scores / probabilities never leave TMEM); the backward
+    # pass recomputes the probabilities.  Needs the tf32 attention path and dh == 128.
+    self.fused_attention = True
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -52,6 +55,18 @@ def _empty(shape, like, dtype=torch.float32):
 class Saved:
   """Activations kept between forward and backward (all torch-owned device tensors)."""
   pass
+
+
+def _attention_probs(cfg, lib, st, qkv, mask, B, H, S, Sp, d, dh, scale, p_att, seed, site, aprec):
+  """Materialised attention probabilities (unfused path, and the backward recompute of the fused
+  one): scores = Q K^T per (b, h) (bert.py:147), then scale + mask + softmax + dropout."""
+  P = _empty((B, H, S, Sp), qkv)
+  gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=B * H, batch_inner=H,
+       a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(H * S * Sp, S * Sp), precision=aprec)
+  Pd = _empty((B, H, S, Sp), qkv) if p_att > 0 else P
+  check(lib.mmt_softmax_mask_fwd(ptr(P), ptr(mask), B, H, S, Sp, scale, p_att, seed, site, ptr(P),
+                                 ptr(Pd) if p_att > 0 else None, st), "mmt_softmax_mask_fwd")
+  return P, Pd
 
 
 def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
@@ -122,18 +137,19 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
     qkv = _empty((BS, 3 * d), flat)
     gemm(BS, 3 * d, d, h, d, 1, flat, d, 1, qkv, 3 * d, b_off=L.off(p + "attention.self.query.weight"),
          bias=flat, bias_off=L.off(p + "attention.self.query.bias"), precision=prec)
-    # K5: scores = Q K^T per (b, h) (bert.py:147)
-    P = _empty((B, H, S, Sp), flat)
-    gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=B * H, batch_inner=H,
-         a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(H * S * Sp, S * Sp), precision=aprec)
-    Pd = _empty((B, H, S, Sp), flat) if p_att > 0 else P
-    check(lib.mmt_softmax_mask_fwd(ptr(P), ptr(sv.mask), B, H, S, Sp, scale, p_att, seed,
-                                   SITE_LAYER + 4 * l, ptr(P), ptr(Pd) if p_att > 0 else None, st),
-          "mmt_softmax_mask_fwd")
-    # ctx = P V, heads merged by the output addressing (bert.py:166-170)
+    fused = cfg.fused_attention and aprec == PREC_TF32 and dh == 128
     ctx = _empty((BS, d), flat)
-    gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx, d, b_off=2 * d, batch=B * H, batch_inner=H,
-         a_bs=(H * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh), precision=aprec)
+    if fused:
+      # K5 fused: softmax(Q K^T / sqrt(dh) + mask) V in one tcgen05 kernel (bert.py:147-170)
+      P = Pd = None
+      check(lib.mmt_attention_fwd(ptr(qkv), ptr(sv.mask), B, H, S, dh, scale, p_att, seed,
+                                  SITE_LAYER + 4 * l, ptr(ctx), None, st), "mmt_attention_fwd")
+    else:
+      P, Pd = _attention_probs(cfg, lib, st, qkv, sv.mask, B, H, S, Sp, d, dh, scale, p_att, seed,
+                               SITE_LAYER + 4 * l, aprec)
+      # ctx = P V, heads merged by the output addressing (bert.py:166-170)
+      gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx, d, b_off=2 * d, batch=B * H, batch_inner=H,
+           a_bs=(H * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh), precision=aprec)
     # K6: attention output dense + dropout + residual + LN (bert.py:186-188)
     z1 = _empty((BS, d), flat)
     gemm(BS, d, d, ctx, d, 1, flat, d, 1, z1, d, b_off=L.off(p + "attention.output.dense.weight"),
@@ -358,7 +374,10 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     dctx = _empty((BS, d), flat)
     gemm(BS, d, d, dt1, d, 1, flat, 1, d, dctx, d, b_off=L.off(p + "attention.output.dense.weight"),
          precision=prec)
-    # --- attention backward (materialised probabilities) ---
+    # --- attention backward (materialised probabilities; recomputed if the forward was fused) ---
+    if ls.P is None:
+      ls.P, ls.Pd = _attention_probs(cfg, lib, st, ls.qkv, sv.mask, B, H, S, Sp, d, dh, scale, p_att, seed,
+                                     SITE_LAYER + 4 * l, aprec)
     dqkv = _empty((BS, 3 * d), flat)
     dP = _empty((B, H, S, Sp), flat)
     bsP = (H * S * Sp, S * Sp)

@@ -578,3 +578,64 @@ def test_train_step_parity_tf32_tensor_core_path(dev, attn):
         (attn, e_conf, e_l2, e_loss, worst[0], worst[1]))
   assert e_conf < TOL and e_l2 < TOL and e_loss < TOL
   assert worst[1] < 1e-2, worst
+
+
+# ------------------------------------------------------------------------------- fused attention
+def _attention_ref(qkv, mask, Bt, Hh, S, dh):
+  d = Hh * dh
+  q, k, v = (qkv[:, i * d:(i + 1) * d].double().view(Bt, S, Hh, dh).permute(0, 2, 1, 3) for i in range(3))
+  sc = q @ k.transpose(-1, -2) / math.sqrt(dh) + (1.0 - mask.double())[:, None, None, :] * -10000.0
+  p = torch.softmax(sc, -1)
+  return (p @ v).permute(0, 2, 1, 3).reshape(Bt * S, d), torch.logsumexp(sc, -1)
+
+
+@pytest.mark.parametrize("Bt,S", [(3, 218), (2, 442), (2, 31), (1, 224), (2, 225)])
+def test_fused_attention_forward_matches_reference(dev, Bt, S):
+  """tcgen05 flash-style attention: one key block (S <= 224) and the online-softmax multi-block
+  path (S = 225, 442 -- BASELINE config C3), ragged last query tile, masked keys."""
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  Hh, dh = 4, 128
+  d = Hh * dh
+  g = torch.Generator().manual_seed(S)
+  qkv = torch.randn(Bt * S, 3 * d, generator=g)
+  mask = (torch.rand(Bt, S, generator=g) > 0.3).float()
+  mask[:, 0] = 1
+  ref, lse_ref = _attention_ref(qkv, mask, Bt, Hh, S, dh)
+  qd, md = qkv.to(dev), mask.to(dev)
+  ctx = torch.full((Bt * S, d), float("nan"), device=dev)
+  lse = torch.empty(Bt, Hh, S, device=dev)
+  _lib.check(lib.mmt_attention_fwd(_lib.ptr(qd), _lib.ptr(md), Bt, Hh, S, dh, 1 / math.sqrt(dh), 0.0, 0, 0,
+                                   _lib.ptr(ctx), _lib.ptr(lse), _lib.stream_ptr()), "attention_fwd")
+  torch.cuda.synchronize()
+  e_ctx, e_lse = H.rel_err(ctx, ref), float((lse.cpu().double() - lse_ref).abs().max())
+  print("fused attention S=%d: ctx rel err %.2e, lse abs err %.2e" % (S, e_ctx, e_lse))
+  assert torch.isfinite(ctx).all()
+  assert e_ctx < 2e-3 and e_lse < 5e-3
+
+
+def test_fused_attention_dropout_matches_unfused_path(dev):
+  """Same (seed, site) -> the fused kernel drops exactly the probabilities the materialised path
+  drops (the backward pass relies on it when it recomputes P)."""
+  from mmt_b200 import _lib, engine
+  lib = _lib.load()
+  Bt, Hh, S, dh = 2, 4, 218, 128
+  d = Hh * dh
+  Sp = (S + 3) // 4 * 4
+  g = torch.Generator().manual_seed(3)
+  qkv = torch.randn(Bt * S, 3 * d, generator=g).to(dev)
+  mask = torch.ones(Bt, S, device=dev)
+  scale, p, seed, site = 1 / math.sqrt(dh), 0.1, 1234567, 20
+  ctx = torch.empty(Bt * S, d, device=dev)
+  _lib.check(lib.mmt_attention_fwd(_lib.ptr(qkv), _lib.ptr(mask), Bt, Hh, S, dh, scale, p, seed, site,
+                                   _lib.ptr(ctx), None, _lib.stream_ptr()), "attention_fwd")
+  P = torch.empty(Bt, Hh, S, Sp, device=dev)
+  _lib.gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=Bt * Hh, batch_inner=Hh,
+            a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(Hh * S * Sp, S * Sp))
+  Pd = torch.empty_like(P)
+  _lib.check(lib.mmt_softmax_mask_fwd(_lib.ptr(P), _lib.ptr(mask), Bt, Hh, S, Sp, scale, p, seed, site,
+                                      _lib.ptr(P), _lib.ptr(Pd), _lib.stream_ptr()), "softmax")
+  ctx2 = torch.empty(Bt * S, d, device=dev)
+  _lib.gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx2, d, b_off=2 * d, batch=Bt * Hh, batch_inner=Hh,
+            a_bs=(Hh * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh))
+  assert H.rel_err(ctx, ctx2) < 2e-3
