@@ -37,6 +37,11 @@ int mmt_version(void);
 int mmt_last_error(char* buf, size_t len);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 int64_t mmt_launch_count(void);
+/* Optional device-resident step counter (uint64, caller-owned; NULL disables): every kernel that
+ * takes a dropout `seed` adds *dev_counter to it and mmt_adam_step adds it to `step`, so a train
+ * step captured in a CUDA graph draws fresh dropout masks / bias corrections on each replay when
+ * the graph increments the counter. */
+int mmt_set_step_counter(const uint64_t* dev_counter);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM:  C(m,n) = epilogue( alpha * sum_k A(m,k) * B(n,k) + bias[n] + add(m,n) )

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mmt_version": (c_i32, []),
     "mmt_last_error": (c_i32, [ctypes.c_char_p, ctypes.c_size_t]),
     "mmt_launch_count": (c_i64, []),
+    "mmt_set_step_counter": (c_i32, [c_p]),
     "mmt_gemm": (c_i32, [ctypes.POINTER(GemmDesc), c_p]),
     "mmt_colsum": (c_i32, [c_p, c_i64, c_i32, c_i64, c_i32, c_i64, c_p, c_i32, c_p]),
     "mmt_embed_ln_fwd": (c_i32, [c_p] * 8 + [c_i32] * 5 + [c_f, c_f, c_u64, c_u32] + [c_p] * 7 + [c_p]),

@@ -9,6 +9,7 @@ namespace mmt {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+const uint64_t* g_step_ctr = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -50,6 +51,11 @@ int mmt_last_error(char* buf, size_t len) {
 }
 
 int64_t mmt_launch_count(void) { return mmt::g_launches.load(); }
+
+int mmt_set_step_counter(const uint64_t* dev_counter) {
+  mmt::g_step_ctr = dev_counter;
+  return 0;
+}
 
 int mmt_gemm(const mmt_gemm_desc* d, void* stream) {
   MMT_ARG_CHECK(d != nullptr, MMT_E_ARG, "mmt_gemm: null descriptor");

@@ -68,6 +68,7 @@ struct AttArgs {
   float p_drop, inv_keep;
   uint64_t seed;
   uint32_t site;
+  const uint64_t* ctr;
 };
 
 // map_qk: qkv viewed as [B*S rows, 3*H*DH cols], box {32 cols, rows<=256}, SWIZZLE_128B
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float* mrow = args.mask + (int64_t)b * S;
     const uint32_t prow = (uint32_t)(((int64_t)b * H + h) * S + qi);   // Philox row id (== unfused path)
+    const uint64_t seed = args.seed + (args.ctr ? *args.ctr : 0);
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * KB;
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
         for (int t4 = 0; t4 < 32; t4 += 4) {
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
           if (args.p_drop > 0.f)
-            sc = dropout_scale4(args.seed, args.site, prow, (uint32_t)((key0 + c * 32 + t4) >> 2), args.p_drop,
+            sc = dropout_scale4(seed, args.site, prow, (uint32_t)((key0 + c * 32 + t4) >> 2), args.p_drop,
                                 args.inv_keep);
           const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
@@ -298,7 +300,7 @@ extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B,
   a.mask_log2 = -10000.0f * 1.44269504088896340736f;
   a.out_scale = tc::kTf32TruncComp;
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  a.seed = seed; a.site = site;
+  a.seed = seed; a.site = site; a.ctr = g_step_ctr;
   constexpr size_t smem = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 64;
   static bool configured = false;
   if (!configured) {

@@ -11,6 +11,9 @@
 namespace mmt {
 
 extern std::atomic<int64_t> g_launches;
+// Optional device-resident step counter (mmt_set_step_counter): kernels add *ctr to their dropout
+// seed / Adam step so a captured CUDA graph draws fresh masks on every replay.
+extern const uint64_t* g_step_ctr;
 
 // ---- error plumbing (no exceptions cross the C ABI) -----------------------------------------
 void set_error(const char* fmt, ...);

@@ -484,8 +484,16 @@ __global__ void max_margin_finish_kernel(int n, float inv_cnt, int fix_norm, flo
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n4, int64_t n, float lr, float b1, float b2,
-                                                   float eps, float wd, float bc1, float bc2_sqrt,
+                                                   float eps, float wd, int step, const uint64_t* __restrict__ ctr,
                                                    float gscale) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const float t = (float)(step + (ctr ? (int)*ctr : 0));      // device-side step counter for graph replays
+    s_bc[0] = 1.f - powf(b1, t);
+    s_bc[1] = sqrtf(1.f - powf(b2, t));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
@@ -637,13 +645,11 @@ int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   MMT_ARG_CHECK(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                 ((uintptr_t)v % 16 == 0), MMT_E_ALIGN, "mmt_adam_step: buffers must be 16-byte aligned");
   if (n == 0) return 0;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale);
   MMT_LAUNCH_CHECK("adam");
   return 0;
 }

@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
     const int32_t* __restrict__ type_idx, const float* __restrict__ pos_emb,
     const float* __restrict__ type_emb, const float* __restrict__ gamma,
     const float* __restrict__ beta, int B, int M, int T, int max_pos, float eps, float p_drop,
-    uint64_t seed, uint32_t site, float* __restrict__ h, float* __restrict__ mask,
+    uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ h, float* __restrict__ mask,
     int32_t* __restrict__ pos_ids, int32_t* __restrict__ type_ids, float* __restrict__ inv_norm,
     float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   const int S = 1 + M * (T + 1);
   const int lane = threadIdx.x & 31;
@@ -94,9 +95,10 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
     const float* __restrict__ inv_norm, const float* __restrict__ mean_i,
     const float* __restrict__ rstd_i, const float* __restrict__ pos_emb,
     const float* __restrict__ type_emb, const float* __restrict__ gamma, int B, int M, int T,
-    float p_drop, uint64_t seed, uint32_t site, float* __restrict__ dproj,
+    float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ dproj,
     float* __restrict__ dpos_emb, float* __restrict__ dtype_emb, float* __restrict__ dgamma,
     float* __restrict__ dbeta) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -179,7 +181,8 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS * 32) res_ln_fwd_kernel(
     float* __restrict__ t, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, int64_t rows, float eps, float p_drop, uint64_t seed,
-    uint32_t site, float* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+    uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -215,9 +218,10 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ z,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
-    const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site,
+    const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr,
     float* __restrict__ dz, float* __restrict__ dt, float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ dbias) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -277,8 +281,9 @@ constexpr int SM_MAXC = 4;   // float4 chunks per lane -> S <= 512
 
 __global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
     const float* __restrict__ scores, const float* __restrict__ mask, int B, int H, int S, int ld,
-    float scale, float p_drop, uint64_t seed, uint32_t site, float* __restrict__ Psoft,
+    float scale, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ Psoft,
     float* __restrict__ Pdrop) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * S;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -333,7 +338,8 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
 
 __global__ void __launch_bounds__(WARPS * 32) softmax_bwd_kernel(
     float* __restrict__ dP, const float* __restrict__ Psoft, int64_t rows, int S, int ld,
-    float scale, float p_drop, uint64_t seed, uint32_t site) {
+    float scale, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const int lane = threadIdx.x & 31;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
@@ -464,7 +470,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ in,
                                                       float* __restrict__ out, int64_t rows, int n4,
-                                                      float p, uint64_t seed, uint32_t site) {
+                                                      float p, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr) {
+  if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const float inv_keep = 1.f / (1.f - p);
   const int64_t total = rows * n4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -498,7 +505,7 @@ int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const
   const int64_t rows = (int64_t)B * (1 + M * (T + 1));
   DISPATCH_VEC(d, (embed_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
       proj, ft, ind, type_idx, pos_emb, type_emb, gamma, beta, B, M, T, max_pos, eps, p_drop, seed,
-      site, h, mask, pos_ids, type_ids, inv_norm, mean, rstd)));
+      site, g_step_ctr, h, mask, pos_ids, type_ids, inv_norm, mean, rstd)));
   MMT_LAUNCH_CHECK("embed_ln_fwd");
   return 0;
 }
@@ -517,7 +524,7 @@ int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   DISPATCH_VEC(d, (embed_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
       dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, M, T, p_drop,
-      seed, site, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
+      seed, site, g_step_ctr, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
   MMT_LAUNCH_CHECK("embed_ln_bwd");
   return 0;
 }
@@ -529,7 +536,7 @@ int mmt_res_ln_fwd(float* t, const float* r, const float* gamma, const float* be
   CHECK_D(d); CHECK_P(p_drop);
   if (rows == 0) return 0;
   DISPATCH_VEC(d, (res_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
-      t, r, gamma, beta, rows, eps, p_drop, seed, site, y, mean, rstd)));
+      t, r, gamma, beta, rows, eps, p_drop, seed, site, g_step_ctr, y, mean, rstd)));
   MMT_LAUNCH_CHECK("res_ln_fwd");
   return 0;
 }
@@ -545,7 +552,7 @@ int mmt_res_ln_bwd(const float* dy, const float* dy2, const float* z, const floa
   int grid = row_grid(rows);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   DISPATCH_VEC(d, (res_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
-      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, dz, dt, dgamma, dbeta, dbias)));
+      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, g_step_ctr, dz, dt, dgamma, dbeta, dbias)));
   MMT_LAUNCH_CHECK("res_ln_bwd");
   return 0;
 }
@@ -559,7 +566,7 @@ int mmt_softmax_mask_fwd(const float* scores, const float* mask, int32_t B, int3
                 "mmt_softmax_mask_fwd: S=%d ld=%d unsupported (S <= %d, ld %% 4 == 0)", S, ld, 128 * SM_MAXC);
   CHECK_P(p_drop);
   softmax_fwd_kernel<<<row_grid((int64_t)B * H * S), WARPS * 32, 0, (cudaStream_t)stream>>>(
-      scores, mask, B, H, S, ld, scale, p_drop, seed, site, Psoft, Pdrop);
+      scores, mask, B, H, S, ld, scale, p_drop, seed, site, g_step_ctr, Psoft, Pdrop);
   MMT_LAUNCH_CHECK("softmax_fwd");
   return 0;
 }
@@ -570,7 +577,7 @@ int mmt_softmax_mask_bwd(float* dP, const float* Psoft, int32_t B, int32_t H, in
   MMT_ARG_CHECK(S > 0 && ld >= S && ld % 4 == 0 && ld <= 128 * SM_MAXC, MMT_E_SHAPE, "mmt_softmax_mask_bwd: S=%d ld=%d unsupported", S, ld);
   CHECK_P(p_drop);
   const int64_t rows = (int64_t)B * H * S;
-  softmax_bwd_kernel<<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(dP, Psoft, rows, S, ld, scale, p_drop, seed, site);
+  softmax_bwd_kernel<<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(dP, Psoft, rows, S, ld, scale, p_drop, seed, site, g_step_ctr);
   MMT_LAUNCH_CHECK("softmax_bwd");
   return 0;
 }
@@ -627,7 +634,7 @@ int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, u
   if (total == 0) return 0;
   int64_t blocks = (total + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  dropout_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n / 4, p, seed, site);
+  dropout_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n / 4, p, seed, site, g_step_ctr);
   MMT_LAUNCH_CHECK("dropout");
   return 0;
 }

@@ -1,0 +1,73 @@
+"""CUDA-graph capture of the whole train step (zero_grad -> forward -> loss -> backward -> Adam).
+
+The step is ~150 kernel launches of 3-300 us each; replaying them as one graph removes the
+per-launch host/driver latency (SURVEY.md §7 "launch count must collapse").  Everything the
+step needs that changes from step to step lives in device memory:
+  * inputs: static device tensors the caller refreshes with `copy_` (or `load()`),
+  * dropout seeds and Adam's bias-correction step: a device counter the graph increments itself
+    (`mmt_set_step_counter`), so every replay draws fresh masks.
+"""
+import torch
+
+from . import _lib
+
+
+class GraphedTrainStep:
+  """graph = GraphedTrainStep(net, crit, opt, example_kwargs, example_text, set_text)
+
+  example_kwargs : dict of CENet.forward kwargs holding DEVICE tensors (kept as the static inputs)
+  set_text(t)    : hands the static text-feature tensor to whatever stands for txt_bert
+  """
+
+  def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3):
+    self.net, self.crit, self.opt = net, crit, opt
+    self.kw, self.text = kwargs, text
+    dev = net.flat.device
+    self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().mmt_set_step_counter(_lib.ptr(self.ctr)), "mmt_set_step_counter")
+    set_text(self.text)
+
+    def one_step():
+      opt.zero_grad()
+      out = net(**self.kw, out="conf", device=dev)
+      loss = crit(out["cross_view_conf_matrix"])
+      loss.backward()
+      opt.step()
+      return loss
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):                       # eager warm-up on the capture stream
+      for _ in range(warmup):
+        one_step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    self.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self.graph):
+      self.ctr.add_(1)
+      self.loss = one_step()
+    # the python-side step counters advanced once during capture; replays advance the device one
+
+  def load(self, kwargs, text):
+    """Refresh the static inputs from other (host-pinned or device) tensors."""
+    for k, v in kwargs.items():
+      if isinstance(v, dict):
+        for m, t in v.items():
+          self.kw[k][m].copy_(t, non_blocking=True)
+      elif torch.is_tensor(v) and torch.is_tensor(self.kw.get(k)) and self.kw[k].is_cuda:
+        self.kw[k].copy_(v, non_blocking=True)
+    self.text.copy_(text, non_blocking=True)
+
+  def replay(self):
+    self.graph.replay()
+    return self.loss
+
+  def close(self):
+    """Back to eager launches: detach the device counter and fold its value into the host-side
+    step counts so Adam's bias correction continues where the replays left off."""
+    torch.cuda.synchronize()
+    n = int(self.ctr.item())
+    _lib.check(_lib.load().mmt_set_step_counter(None), "mmt_set_step_counter")
+    if hasattr(self.opt, "t"):
+      self.opt.t += n
+    self.net._step += n

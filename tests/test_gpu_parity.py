@@ -639,3 +639,43 @@ def test_fused_attention_dropout_matches_unfused_path(dev):
   _lib.gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx2, d, b_off=2 * d, batch=Bt * Hh, batch_inner=Hh,
             a_bs=(Hh * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh))
   assert H.rel_err(ctx, ctx2) < 2e-3
+
+
+def test_graphed_train_step_matches_eager_and_draws_fresh_dropout(dev):
+  """The CUDA-graph replay of the whole train step gives the eager step's loss (p = 0) and, with
+  dropout, a different mask on every replay (device-side step counter)."""
+  from mmt_b200 import _lib
+  from mmt_b200.graph import GraphedTrainStep
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  from mmt_b200.optim import FusedAdam
+  for p_drop in (0.0, 0.1):
+    ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish"], 8, 14, layers=2, dropout=p_drop)
+    crit = MaxMarginRankingLoss(0.05, True)
+    nets, losses = [], []
+    for graphed in (False, True):
+      net = H.build_cuda_net(ed, vb, P, batch, dropout=p_drop, precision="tf32").train()
+      net._step = 0
+      opt = FusedAdam(net, lr=1e-4)
+      kw = H.batch_kwargs(batch, "cuda")
+      ls = []
+      if graphed:
+        g = GraphedTrainStep(net, crit, opt, kw, net.txt_bert.hidden[:, 0].clone(), lambda t: None, warmup=2)
+        for _ in range(3):
+          ls.append(float(g.replay()))
+        g.close()
+      else:
+        for _ in range(5):
+          opt.zero_grad()
+          l = crit(net(**kw)["cross_view_conf_matrix"])
+          l.backward()
+          opt.step()
+          ls.append(float(l))
+      losses.append(ls)
+    eager, graph = losses
+    if p_drop == 0.0:
+      # replays 1..3 == eager steps 3..5 (two eager warm-up steps preceded the capture)
+      for a, b in zip(eager[2:], graph):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(a)), (eager, graph)
+    else:
+      assert len(set(round(x, 7) for x in graph)) == len(graph), graph      # fresh masks each replay
+      assert all(math.isfinite(x) for x in graph)
