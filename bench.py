@@ -235,9 +235,9 @@ def run_b200(args):
     return float(ms)
 
   # ---- device-resident throughput ("value") ----
-  # The step is replayed as ONE CUDA graph (mmt_b200/graph.py); the static input tensors are
+  # With --graph the step is replayed as ONE CUDA graph (mmt_b200/graph.py): static input tensors
   # refreshed from the ring of resident batches with device-to-device copies inside the timed
-  # region, dropout seeds / Adam step advance through a device counter.
+  # region, dropout seeds / Adam step advancing through a device counter.
   for i in range(args.warmup):
     step(*resident[i % NB])
   n0 = _lib.launch_count()
@@ -245,7 +245,7 @@ def run_b200(args):
   torch.cuda.synchronize()
   launches_per_step = _lib.launch_count() - n0
   graphed = None
-  if not args.no_graph:
+  if args.graph:
     from mmt_b200.graph import GraphedTrainStep
     skw = {k: ({m: t.clone() for m, t in v.items()} if isinstance(v, dict) else v)
            for k, v in resident[0][0].items()}
@@ -517,7 +517,9 @@ def main():
   ap.add_argument("--precision", default=os.environ.get("MMT_PRECISION", "tf32"),
                   choices=["fp32", "tf32"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA graph")
+  ap.add_argument("--graph", action="store_true",
+                  help="replay the step as one CUDA graph for `value` (mmt_b200/graph.py); measured gain on "
+                       "B200 is < 1 % because the step is GPU-bound, so eager launches are the default")
   ap.add_argument("--no-hbm-probe", action="store_true")
   args = ap.parse_args()
   if args.impl == "reference":
