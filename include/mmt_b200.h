@@ -81,6 +81,10 @@ typedef struct mmt_gemm_desc {
   int64_t a_bs0, a_bs1, b_bs0, b_bs1, c_bs0, c_bs1;
   int64_t bias_bs;      /* bias of batch z starts at bias + z*bias_bs */
   int32_t precision;
+  float* colsum;        /* optional (MMT_PREC_TF32 only): colsum[z1*colsum_bs + n] += sum_m C(m,n) of the
+                           FINAL output values, accumulated atomically by the epilogue -- the bias
+                           gradient of the layer whose input gradient this GEMM produces.  Caller zeroes it. */
+  int64_t colsum_bs;
   int32_t flags;        /* MMT_GEMM_SPLIT_K: allow a split-K schedule (fp32 atomics, run-to-run
                            summation order not fixed); forward GEMMs leave it clear so that the
                            forward pass is bit-reproducible */

@@ -36,6 +36,7 @@ class GemmDesc(ctypes.Structure):
       ("c_bs0", c_i64), ("c_bs1", c_i64),
       ("bias_bs", c_i64),
       ("precision", c_i32),
+      ("colsum", c_p), ("colsum_bs", c_i64),
       ("flags", c_i32),
   ]
 
@@ -124,7 +125,8 @@ def launch_count():
 def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_off=0, bias=None,
          bias_off=0, add=None, add_off=0, aux=None, aux_off=0, epilogue=EPI_NONE, alpha=1.0,
          a_kb=0, a_kbs=0, c_mb=0, c_mbs=0, batch=1, batch_inner=1, a_bs=(0, 0), b_bs=(0, 0),
-         c_bs=(0, 0), bias_bs=0, precision=PREC_FP32, split_k=False):
+         c_bs=(0, 0), bias_bs=0, precision=PREC_FP32, split_k=False, colsum=None, colsum_off=0,
+         colsum_bs=0):
   d = GemmDesc()
   d.M, d.N, d.K = M, N, K
   d.A, d.a_ms, d.a_ks, d.a_kb, d.a_kbs = ptr(A, a_off), a_ms, a_ks, a_kb, a_kbs
@@ -141,4 +143,6 @@ def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_
   d.bias_bs = bias_bs
   d.precision = precision
   d.flags = GEMM_SPLIT_K if split_k else 0
+  d.colsum = ptr(colsum, colsum_off)
+  d.colsum_bs = colsum_bs
   check(load().mmt_gemm(ctypes.byref(d), stream_ptr()), "mmt_gemm")

@@ -148,9 +148,75 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmArgs args) {
   }
 }
 
+// 32 x 32 x 16 tiles for small outputs (the per-expert similarity dot products at training batch
+// sizes: M = N = 64, K = 512, 7 batches): 16x more CTAs than the 128-tile kernel, which for these
+// shapes is pure latency.  One thread = 2 x 2 outputs; fp32 FMAs in k order.
+constexpr int SB = 32;
+__global__ void __launch_bounds__(NT) sgemm_small_kernel(const GemmArgs args) {
+  const mmt_gemm_desc& d = args.d;
+  __shared__ float As[BK][SB + 1];
+  __shared__ float Bs[BK][SB + 1];
+  const int tid = threadIdx.x;
+  const int z = blockIdx.z;
+  const int z0 = z / d.batch_inner, z1 = z % d.batch_inner;
+  const float* __restrict__ A = d.A + z0 * d.a_bs0 + z1 * d.a_bs1;
+  const float* __restrict__ B = d.B + z0 * d.b_bs0 + z1 * d.b_bs1;
+  const int64_t c_base = z0 * d.c_bs0 + z1 * d.c_bs1;
+  const int m0 = blockIdx.y * SB, n0 = blockIdx.x * SB;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < d.K; k0 += BK) {
+    // 32 x 16 elements per operand = 512 / 256 threads = 2 each; k fastest when contiguous along k
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * NT;
+      int mm, kk;
+      if (d.a_ks == 1) { kk = e % BK; mm = e / BK; } else { mm = e % SB; kk = e / SB; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < d.M && k < d.K) ? __ldg(A + a_off(d, m, k)) : 0.f;
+      int nn;
+      if (d.b_ks == 1) { kk = e % BK; nn = e / BK; } else { nn = e % SB; kk = e / SB; }
+      const int n = n0 + nn, k2 = k0 + kk;
+      Bs[kk][nn] = (n < d.N && k2 < d.K) ? __ldg(B + (int64_t)n * d.b_ns + (int64_t)k2 * d.b_ks) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float a0 = As[k][ty], a1 = As[k][ty + 16], b0 = Bs[k][tx], b1 = Bs[k][tx + 16];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= d.M) continue;
+    const int64_t row = c_base + c_off(d, m);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= d.N) continue;
+      float v = acc[i][j] * d.alpha;
+      if (d.bias) v += __ldg(d.bias + z * d.bias_bs + n);
+      if (d.add) v += d.add[row + n];
+      if (d.epilogue == MMT_EPI_GELU) { d.aux[row + n] = v; v = gelu_erf(v); }
+      else if (d.epilogue == MMT_EPI_DGELU) v *= dgelu_erf(d.aux[row + n]);
+      d.C[row + n] = v;
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
+  if (d.M <= 96 && d.N <= 96) {                     // small outputs: 32 x 32 tiles
+    GemmArgs small{d, 1, 0};
+    dim3 g((d.N + SB - 1) / SB, (d.M + SB - 1) / SB, d.batch);
+    sgemm_small_kernel<<<g, NT, 0, stream>>>(small);
+    MMT_LAUNCH_CHECK("sgemm_small_kernel");
+    return 0;
+  }
   GemmArgs args{d, 1, ((d.K + BK - 1) / BK) * BK};
   const int tiles = ((d.N + BN - 1) / BN) * ((d.M + BM - 1) / BM);
   // weight-gradient shape: few output tiles, long K, dense un-batched C that is not also `add`

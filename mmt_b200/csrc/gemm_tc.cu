@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       float v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);   // warp-collective
       const int nb = n0 + c * 32;
-      if (!row_ok || nb >= d.N) continue;
+      const bool active = row_ok && nb < d.N;
+      if (active) {
       float* crow = d.C + row + nb;
       const float* addrow = d.add ? d.add + row + nb : nullptr;
       float* auxrow = d.aux ? d.aux + row + nb : nullptr;
@@ -219,7 +220,21 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (ok[q]) crow[j + q] = o[q];
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[j + q] = ok[q] ? o[q] : 0.f;       // final values, for the column sums
       }
+      }  // active
+      if (d.colsum != nullptr && args.split_k == 1) {
+      // fused bias gradient: lane t ends up with the sum over this warp's 32 rows of column t
+      // (warp-collective: executed by all lanes, rows / columns out of range contribute 0)
+      float mine = 0.f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float sv = warp_sum(active ? v[t] : 0.f);
+        if (lane == t) mine = sv;
+      }
+      if (nb + lane < d.N) atomicAdd(d.colsum + (int64_t)z1 * d.colsum_bs + nb + lane, mine);
+    }
     }
     tc_fence_before();
   }

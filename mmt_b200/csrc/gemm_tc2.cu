@@ -222,6 +222,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) if (ok[i]) *reinterpret_cast<float4*>(d.C + off[i]) = o[i];
+            if (d.colsum != nullptr) {                        // fused bias gradient: column sums of the output
+              float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (ok[i]) { cs.x += o[i].x; cs.y += o[i].y; cs.z += o[i].z; cs.w += o[i].w; }
+#pragma unroll
+              for (int sh = 8; sh <= 16; sh <<= 1) {          // lanes sharing sub_c differ in bits 3,4
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, sh); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, sh);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, sh); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, sh);
+              }
+              if (sub_r == 0 && col < d.N)
+                atomicAdd(reinterpret_cast<float4*>(d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + col), cs);
+            }
           }
         } else {
           // ragged right edge / unaligned C: predicated scalars
@@ -238,6 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
               if (d.epilogue == MMT_EPI_GELU) { d.aux[off[i] + t] = val; val = gelu_fast(val); }
               else if (d.epilogue == MMT_EPI_DGELU) val *= dgelu_fast(d.aux[off[i] + t]);
               d.C[off[i] + t] = val;
+              if (d.colsum != nullptr) atomicAdd(d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + col + t, val);
             }
           }
         }

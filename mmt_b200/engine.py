@@ -350,12 +350,15 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     gemm(d, ff, BS, dt2, 1, d, ls.f, 1, ff, gflat, ff, c_off=L.off(p + "output.dense.weight"),
          precision=prec, split_k=True)
     du = _empty((BS, ff), flat)
+    fuse_cs = (prec == PREC_TF32)        # bias gradients as a fused column-sum epilogue (tensor-core path)
     gemm(BS, ff, d, dt2, d, 1, flat, 1, ff, du, ff, b_off=L.off(p + "output.dense.weight"),
-         epilogue=EPI_DGELU, aux=ls.u, precision=prec)
+         epilogue=EPI_DGELU, aux=ls.u, precision=prec,
+         colsum=gflat if fuse_cs else None, colsum_off=L.off(p + "intermediate.dense.bias"))
     # FFN up: dW1 [ff, d] = du^T @ a ; db1 = colsum(du) ; da = du @ W1
     gemm(ff, d, BS, du, 1, ff, ls.a, 1, d, gflat, d, c_off=L.off(p + "intermediate.dense.weight"),
          precision=prec, split_k=True)
-    colsum(du, BS, ff, ff, L.off(p + "intermediate.dense.bias"))
+    if not fuse_cs:
+      colsum(du, BS, ff, ff, L.off(p + "intermediate.dense.bias"))
     da = _empty((BS, d), flat)
     gemm(BS, d, ff, du, ff, 1, flat, 1, d, da, d, b_off=L.off(p + "intermediate.dense.weight"),
          precision=prec)
@@ -386,19 +389,26 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     gemm(S, S, dh, dctx, d, 1, ls.qkv, 3 * d, 1, dP, Sp, b_off=2 * d, batch=B * H, batch_inner=H,
          a_bs=(S * d, dh), b_bs=bsQ, c_bs=bsP, precision=aprec)
     # dV = Pd^T @ dctx
+    fuse_acs = (aprec == PREC_TF32)
+    acs = dict(colsum=gflat, colsum_bs=dh) if fuse_acs else {}
+    qb_off = L.off(p + "attention.self.query.bias")
     gemm(S, dh, S, ls.Pd, 1, Sp, dctx, 1, d, dqkv, 3 * d, c_off=2 * d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=(S * d, dh), c_bs=bsQ, precision=aprec)
+         a_bs=bsP, b_bs=(S * d, dh), c_bs=bsQ, precision=aprec,
+         **(dict(acs, colsum_off=qb_off + 2 * d) if fuse_acs else {}))
     check(lib.mmt_softmax_mask_bwd(ptr(dP), ptr(ls.P), B, H, S, Sp, scale, p_att, seed,
                                    SITE_LAYER + 4 * l, st), "mmt_softmax_mask_bwd")
     # dQ = dS @ K ; dK = dS^T @ Q
     gemm(S, dh, S, dP, Sp, 1, ls.qkv, 1, 3 * d, dqkv, 3 * d, b_off=d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec)
+         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec,
+         **(dict(acs, colsum_off=qb_off) if fuse_acs else {}))
     gemm(S, dh, S, dP, 1, Sp, ls.qkv, 1, 3 * d, dqkv, 3 * d, c_off=d, batch=B * H, batch_inner=H,
-         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec)
+         a_bs=bsP, b_bs=bsQ, c_bs=bsQ, precision=aprec,
+         **(dict(acs, colsum_off=qb_off + d) if fuse_acs else {}))
     # QKV projection: dWqkv [3d, d] = dqkv^T @ h_in ; dbqkv ; dh = dz1 + dqkv @ Wqkv
     gemm(3 * d, d, BS, dqkv, 1, 3 * d, ls.h_in, 1, d, gflat, d,
          c_off=L.off(p + "attention.self.query.weight"), precision=prec, split_k=True)
-    colsum(dqkv, BS, 3 * d, 3 * d, L.off(p + "attention.self.query.bias"))
+    if not fuse_acs:
+      colsum(dqkv, BS, 3 * d, 3 * d, L.off(p + "attention.self.query.bias"))
     dh_ = _empty((BS, d), flat)
     gemm(BS, d, 3 * d, dqkv, 3 * d, 1, flat, 1, d, dh_, d,
          b_off=L.off(p + "attention.self.query.weight"), add=dz1, precision=prec)
