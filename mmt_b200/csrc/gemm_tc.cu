@@ -16,6 +16,8 @@
 // along m / n); the latter is what the backward GEMMs (dgrad: B = W read "transposed"; wgrad:
 // A = dY^T, B = X^T) need, so no transposes are ever materialised.  The UMMA shared-memory
 // descriptors and the TMA boxes are built per layout (canonical SWIZZLE_128B atoms).
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace mmt {
@@ -332,6 +334,7 @@ int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }
 
 int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
+int gemm_tc_pair(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
 
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(d.batch % d.batch_inner == 0, MMT_E_SHAPE, "gemm_tc: batch %d not a multiple of batch_inner %d",
@@ -341,6 +344,14 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(!a_mn || d.a_ms == 1, MMT_E_UNSUPPORTED, "gemm_tc: A must be contiguous along k or m");
   MMT_ARG_CHECK(!b_mn || d.b_ns == 1, MMT_E_UNSUPPORTED, "gemm_tc: B must be contiguous along k or n");
   MMT_ARG_CHECK(d.K >= 1, MMT_E_SHAPE, "gemm_tc: K=%d", d.K);
+  {
+    static const bool use_pair = [] { const char* e = getenv("MMT_GEMM_PAIR"); return e && e[0] == '1'; }();
+    if (use_pair) {                          // CTA-pair (cta_group::2) 256x256 kernel
+      bool taken = false;
+      int prc = gemm_tc_pair(d, stream, &taken);
+      if (prc != 0 || taken) return prc;
+    }
+  }
   {
     bool taken = false;                      // large un-batched problems: persistent 128x256 kernel
     int prc = gemm_tc_persistent(d, stream, &taken);
