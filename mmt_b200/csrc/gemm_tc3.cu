@@ -62,14 +62,28 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {       // arrive
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                : "memory");
 }
+// tempty arrivals only order TMEM reads (tcgen05.wait::ld + tcgen05.fence::before_thread_sync do that),
+// not this warp's global stores: .relaxed keeps the epilogue from draining its stores (MEMBAR) per tile.
 __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {  // arrive on the leader CTA's copy of `bar`
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                           // two warps per TMEM lane quarter, half the columns each
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr int STG_PITCH = 36;                         // floats; 16 B aligned rows, conflict-free v4 phases
 constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
@@ -85,7 +99,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Tc3Args args) {
-  constexpr int BN = 256, BNH = 128, STAGES = 6;
+  constexpr int BN = 256, BNH = 128, STAGES = 5;
   constexpr uint32_t B_BYTES = BNH * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -93,7 +107,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
@@ -106,7 +120,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }  // 4 warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }  // every epilogue warp of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -196,9 +210,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                               // TMEM lane quarter == output rows 32q..32q+31
-    float* stg = staging + q * (32 * STG_PITCH);
+    const int chalf = (warp - 2) >> 2;                    // which half of the 256 columns this warp drains
+    const uint32_t stg = smem_u32(staging) + (uint32_t)(warp - 2) * STG_BYTES_PER_WARP;
     const bool vec_ok = ((d.c_ms & 3) == 0) && (((d.c_bs0 | d.c_bs1 | d.bias_bs) & 3) == 0) &&
                         ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
     const int sub_r = lane >> 3;                          // store phase: row within a group of 4
@@ -215,7 +230,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int nb = n0 + c * 32;
         if (nb >= d.N) break;                             // warp-uniform
         float v[32];
@@ -223,8 +238,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // phase 1: this lane's row -> warp-private staging (row pitch 36 floats)
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) =
-              make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha);
+          sts128(stg + (uint32_t)(lane * STG_PITCH + j) * 4,
+                 make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha));
         __syncwarp();
         // phase 2: coalesced: lanes 8r..8r+7 cover one 128-byte row segment
         const int col = nb + sub_c;
@@ -246,7 +261,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const int m = m0 + (int)rank * BM + q * 32 + rl;
           ok[i] = (m < d.M) && (col < d.N);
           off[i] = zoff + (int64_t)m * d.c_ms + col;
-          o[i] = *reinterpret_cast<const float4*>(stg + rl * STG_PITCH + sub_c);
+          o[i] = lds128(stg + (uint32_t)(rl * STG_PITCH + sub_c) * 4);
           o[i].x += bv[0]; o[i].y += bv[1]; o[i].z += bv[2]; o[i].w += bv[3];
         }
         if (full) {
@@ -316,7 +331,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                                       // this warp no longer reads the accumulator
-        if (leader) mbar_arrive(&tempty_bar[buf]); else mbar_arrive_on_leader(&tempty_bar[buf]);
+        if (leader) mbar_arrive_relaxed(&tempty_bar[buf]); else mbar_arrive_on_leader(&tempty_bar[buf]);
       }
     }
   }
@@ -330,7 +345,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 template <bool A_MN, bool B_MN>
 int launch3(const CUtensorMap& ma, const CUtensorMap& mb, const Tc3Args& args, cudaStream_t stream) {
-  constexpr size_t smem = 6 * (A_BYTES + 128 * BK * 4) + 4 * STG_BYTES_PER_WARP + 1024 + 256;
+  constexpr size_t smem = 5 * (A_BYTES + 128 * BK * 4) + EPI_WARPS * STG_BYTES_PER_WARP + 1024 + 256;
   static bool configured = false;
   auto kern = gemm_tc3_kernel<A_MN, B_MN>;
   if (!configured) {
