@@ -345,7 +345,8 @@ int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream) {
   MMT_ARG_CHECK(!b_mn || d.b_ns == 1, MMT_E_UNSUPPORTED, "gemm_tc: B must be contiguous along k or n");
   MMT_ARG_CHECK(d.K >= 1, MMT_E_SHAPE, "gemm_tc: K=%d", d.K);
   {
-    static const bool use_pair = [] { const char* e = getenv("MMT_GEMM_PAIR"); return e && e[0] == '1'; }();
+    // CTA-pair kernel by default; MMT_GEMM_PAIR=0 keeps large problems on the 1-CTA persistent kernel
+    static const bool use_pair = [] { const char* e = getenv("MMT_GEMM_PAIR"); return !(e && e[0] == '0'); }();
     if (use_pair) {                          // CTA-pair (cta_group::2) 256x256 kernel
       bool taken = false;
       int prc = gemm_tc_pair(d, stream, &taken);
