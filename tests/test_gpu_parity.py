@@ -679,3 +679,26 @@ def test_graphed_train_step_matches_eager_and_draws_fresh_dropout(dev):
     else:
       assert len(set(round(x, 7) for x in graph)) == len(graph), graph      # fresh masks each replay
       assert all(math.isfinite(x) for x in graph)
+
+
+@pytest.mark.parametrize("name,kw", [
+    # BASELINE configs[2]: ActivityNet geometry, 7 experts, T=62 -> S=442 (two key blocks in the fused
+    # attention kernel), max_position_embeddings 102, type_vocab 10
+    ("C3-activitynet-S442", dict(modalities=["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"],
+                                 B=3, T=62, layers=2, max_pos=102, type_vocab=10)),
+    # BASELINE configs[4] geometry: LSMDC (face_dim 128, type_vocab 10)
+    ("C5-lsmdc-face128", dict(modalities=["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"],
+                              B=4, T=30, layers=2, max_pos=32, type_vocab=10, face_dim=128)),
+])
+def test_other_baseline_geometries_tf32(dev, name, kw):
+  from mmt_b200.model.loss import MaxMarginRankingLoss
+  ed, vb, P, batch, cfg = H.make_case(**kw)
+  ref = O.cenet_forward(P, batch, cfg, training=True, out="conf", text_feat=batch["text_feat"])
+  net = H.build_cuda_net(ed, vb, P, batch, precision="tf32").train()
+  out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]
+  MaxMarginRankingLoss(0.05, True)(out).backward()
+  torch.cuda.synchronize()
+  e = H.rel_err(out, ref["cross_view_conf_matrix"])
+  print("%s: conf max-rel %.2e" % (name, e))
+  assert e < 2e-3          # tiny batches: the max-norm figure of a 3x3 / 4x4 matrix is noisy
+  assert all(torch.isfinite(p.grad).all() for p in net._hot_params() if p.grad is not None)
