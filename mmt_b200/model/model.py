@@ -331,6 +331,10 @@ class CENet(nn.Module):
       raise RuntimeError("mmt_b200.CENet needs a CUDA device (no CPU fallback); call .to('cuda')")
     mods = self.modalities
     b, caps = token_ids.size(0), token_ids.size(1)
+    if self.training and b * caps == 1 and not self._dp:
+      # torch.nn.BatchNorm1d (text_GU.*.cg.batch_norm) refuses a single row in training mode
+      raise ValueError("Expected more than 1 value per channel when training, got input size "
+                       "torch.Size([1, %d])" % self.same_dim)
     text = self._text_features(token_ids, dev).to(torch.float32).contiguous()
 
     def prep(x):

@@ -702,3 +702,33 @@ def test_other_baseline_geometries_tf32(dev, name, kw):
   print("%s: conf max-rel %.2e" % (name, e))
   assert e < 2e-3          # tiny batches: the max-norm figure of a 3x3 / 4x4 matrix is noisy
   assert all(torch.isfinite(p.grad).all() for p in net._hot_params() if p.grad is not None)
+
+
+def test_eval_scale_similarity_indep(dev):
+  """Evaluation-scale call of sharded_cross_view_inner_product (trainer/trainer.py:396-403):
+  300 videos x 20 captions, CPU tensors in, 'indep' merge; t2v ranks equal the oracle's."""
+  from mmt_b200.model.model import sharded_cross_view_inner_product
+  g = torch.Generator().manual_seed(8)
+  mods = ["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"]
+  nv, caps, d = 300, 20, 512
+  vid = {m: torch.nn.functional.normalize(torch.randn(nv, d, generator=g), dim=-1) for m in mods}
+  txt = {m: torch.nn.functional.normalize(torch.randn(nv, caps, d, generator=g), dim=-1) for m in mods}
+  vw = torch.full((nv, len(mods)), 1.0 / len(mods))
+  tw = torch.softmax(torch.randn(nv, caps, len(mods), generator=g), -1)
+  ref = O.sharded_cross_view_inner_product(vid, txt, vw, tw, mods, "indep")
+  got = sharded_cross_view_inner_product(vid, {m: v.clone() for m, v in txt.items()}, vw, tw, mods, "indep")
+  assert got.device.type == "cpu" and tuple(got.shape) == (nv * caps, nv)
+  np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=0, atol=2e-6)
+  r1, r2 = O.retrieval_ranks(got.numpy()), O.retrieval_ranks(ref.numpy())
+  assert float(np.mean(r1 == r2)) > 0.999           # identical up to exact fp32 ties
+
+
+def test_single_sample_training_batch_raises_like_batchnorm(dev):
+  ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish"], 1, 6, layers=1)
+  net = H.build_cuda_net(ed, vb, P, batch).train()
+  with pytest.raises(ValueError, match="more than 1 value per channel"):
+    net(**H.batch_kwargs(batch, "cuda"))
+  net.eval()
+  with torch.no_grad():
+    out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]     # eval: running stats
+  assert tuple(out.shape) == (1, 1) and torch.isfinite(out).all()
