@@ -52,6 +52,16 @@ def _empty(shape, like, dtype=torch.float32):
   return torch.empty(shape, device=like.device, dtype=dtype)
 
 
+_SIDE = {}
+
+
+def _side_streams(device, n):
+  key = (device.index, n)
+  if key not in _SIDE:
+    _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+  return _SIDE[key]
+
+
 class Saved:
   """Activations kept between forward and backward (all torch-owned device tensors)."""
   pass
@@ -82,7 +92,6 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   B, T = feats[0].shape[0], feats[0].shape[1]
   S = 1 + M * (T + 1)
   BS = B * S
-  st = stream_ptr()
   lib = _lib.load()
   prec = cfg.precision
   aprec = cfg.precision if cfg.attn_precision is None else cfg.attn_precision
@@ -96,20 +105,40 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   # rows are packed as one [B, T+1, in] operand so the projection (and its weight gradient) is a
   # single dense GEMM; outputs are expert-major [M, B, T+1, d] and gathered into token order by
   # the embedding kernel.
+  # The M projections are independent and each fills only ~1/5 of the SMs (1984 x 512 outputs), so
+  # they are issued round-robin on a few side streams and joined before the embedding kernel.
   R1 = B * (T + 1)
   proj = _empty((M, R1, d), flat)
-  sv.xpack = []
+  sv.xpack = [_empty((B, T + 1, cfg.in_dims[k]), flat) for k in range(M)]   # allocated on the main stream
+  main = torch.cuda.current_stream() if flat.is_cuda else None
+  side = _side_streams(flat.device, min(4, M)) if (flat.is_cuda and M > 1) else []
+  if side:
+    fork = torch.cuda.Event()
+    fork.record(main)
   for k, mod in enumerate(cfg.mods):
     w_off = L.off("video_dim_reduce.%s.fc.weight" % mod)
     b_off = L.off("video_dim_reduce.%s.fc.bias" % mod)
     din = cfg.in_dims[k]
-    xp = torch.cat((maxp[k].unsqueeze(1), feats[k]), 1)          # [B, T+1, in] (data movement only)
-    sv.xpack.append(xp)
-    gemm(R1, d, din, xp, din, 1, flat, din, 1, proj, d, b_off=w_off, bias=flat, bias_off=b_off,
-         c_off=k * R1 * d, precision=prec)
+    xp = sv.xpack[k]
+
+    def project():
+      torch.cat((maxp[k].unsqueeze(1), feats[k]), 1, out=xp)    # [B, T+1, in] (data movement only)
+      gemm(R1, d, din, xp, din, 1, flat, din, 1, proj, d, b_off=w_off, bias=flat, bias_off=b_off,
+           c_off=k * R1 * d, precision=prec)
+
+    if side:
+      st_k = side[k % len(side)]
+      st_k.wait_event(fork)
+      with torch.cuda.stream(st_k):
+        project()
+    else:
+      project()
+  for st_k in side:
+    main.wait_stream(st_k)
   sv.proj = proj
 
   # ---- K2+K3: token assembly + BertEmbeddings (model.py:485-567, bert.py:87-105) ----
+  st = stream_ptr()
   h = _empty((BS, d), flat)
   sv.mask = _empty((BS,), flat)
   sv.pos_ids = _empty((BS,), flat, torch.int32)
