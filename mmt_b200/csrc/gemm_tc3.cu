@@ -13,9 +13,14 @@
 //                              bias / residual / erf-GELU / GELU' and fully coalesced 128-bit
 //                              global loads/stores (each store instruction covers 4 complete
 //                              128-byte row segments)
-// Tiles are ordered m-fastest so the CTAs that run together share the same B (weight) tile in L2.
+// Tiles are rasterised in groups of 2 m-tiles x all n-tiles, so the 74 pairs that run together read
+// few distinct A (activation) row blocks as well as few B (weight) tiles: the fp32-operand main loop
+// is bound by L2 -> SM traffic (~9 TB/s aggregate measured), and concurrent readers of the same lines
+// are cheaper than distinct streams (measured 3-8 % faster than m-fastest on the encoder's shapes).
 // Weight-gradient shapes (few tiles, K = B*S) are split along K into (tile, k-range) work items
 // whose epilogue reduces with red.global.add.v4.f32 into a zeroed C.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace mmt {
@@ -92,6 +97,7 @@ struct Tc3Args {
   mmt_gemm_desc d;
   int num_m_tiles, num_n_tiles;
   int split_k, kb_per_split, num_kb;
+  int group_m;                                          // rasterisation: m-tiles per group (n advances inside a group)
 };
 
 // Pair tile 256 (m) x 256 (n); per CTA and stage: A 128x32 + B 128x32 fp32 = 32 KB, 6 stages.
@@ -137,8 +143,12 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     z = w / (num_tiles * args.split_k);
     w -= z * num_tiles * args.split_k;
     const int tile = w / args.split_k, ks = w % args.split_k;
-    n0 = (tile / args.num_m_tiles) * BN;
-    m0 = (tile % args.num_m_tiles) * (2 * BM);            // pair tile: 256 rows
+    // grouped rasterisation: groups of group_m m-tiles; inside a group m runs fastest, then n
+    const int per_group = args.group_m * args.num_n_tiles;
+    const int grp = tile / per_group, in_grp = tile - grp * per_group;
+    const int gm = min(args.group_m, args.num_m_tiles - grp * args.group_m);   // last group may be short
+    n0 = (in_grp / gm) * BN;
+    m0 = (grp * args.group_m + in_grp % gm) * (2 * BM);   // pair tile: 256 rows
     kb0 = ks * args.kb_per_split;
     nkb = min(args.num_kb, kb0 + args.kb_per_split) - kb0;
   };
@@ -379,6 +389,9 @@ int gemm_tc_pair(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken) {
   args.num_kb = (d.K + BK - 1) / BK;
   args.split_k = 1;
   args.kb_per_split = args.num_kb;
+  static const int group_m_env = [] { const char* e = getenv("MMT_PAIR_GROUP_M"); return e ? atoi(e) : 0; }();  // tuning switch
+  args.group_m = group_m_env > 0 ? group_m_env : 2;
+  if (args.group_m > args.num_m_tiles) args.group_m = args.num_m_tiles;
   const int tiles = args.num_m_tiles * args.num_n_tiles;
   const int max_pairs = num_sms() / 2;
   const bool can_split = (d.flags & MMT_GEMM_SPLIT_K) && d.c_ms == d.N && d.epilogue == MMT_EPI_NONE &&

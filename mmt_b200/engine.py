@@ -342,9 +342,11 @@ def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
   return dtext
 
 
-def video_backward(cfg, flat, gflat, sv, dvid):
+def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
   """Backward of video_forward: every video-side parameter gradient into `gflat` (small region
-  accumulated -- zero it first with zero_small_grads -- big matrices overwritten)."""
+  accumulated -- zero it first with zero_small_grads -- big matrices overwritten).
+  `on_layer_done(l)` is called once layer l's weight-matrix gradients have been enqueued (the
+  data-parallel path starts their all-reduce there)."""
   L = cfg.layout
   d, ff, H, dh, M = cfg.d, cfg.ff, cfg.H, cfg.dh, cfg.M
   B, T, S, Sp = sv.B, sv.T, sv.S, sv.Sp
@@ -441,6 +443,8 @@ def video_backward(cfg, flat, gflat, sv, dvid):
     dh_ = _empty((BS, d), flat)
     gemm(BS, d, 3 * d, dqkv, 3 * d, 1, flat, 1, d, dh_, d,
          b_off=L.off(p + "attention.self.query.weight"), add=dz1, precision=prec)
+    if on_layer_done is not None:
+      on_layer_done(l)
 
   # --- embeddings + token assembly backward ---
   R1 = B * (T + 1)

@@ -9,7 +9,11 @@ steps per train step:
             text features [B/W, text_dim] -- after which every rank evaluates the (tiny) text head,
             similarity matrix and loss on the GLOBAL batch, so BatchNorm statistics and the loss
             are exactly those of the single-device reference at batch B (no SyncBN collective);
-  backward: ONE all-reduce(SUM) of the flat gradient buffer.  Encoder gradients are per-rank
+  backward: all-reduce(SUM) of the flat gradient buffer, issued in a few contiguous pieces as
+            they become final -- the head's runs right after the head backward, each encoder
+            layer's weight-gradient block when that layer's backward has been enqueued, the rest
+            (biases, LayerNorm, embeddings, ReduceDim) at the end -- so that NCCL runs on its own
+            stream underneath the remaining backward kernels.  Encoder gradients are per-rank
             partial sums of the global-mean loss; head gradients are identical on every rank and
             are pre-scaled by 1/W (exact for W a power of two) so the same SUM leaves them intact.
 """
@@ -39,6 +43,33 @@ def head_segments(layout):
   return runs
 
 
+class GradReducer:
+  """Asynchronous all-reduce of disjoint pieces of one flat gradient buffer.  `reduce(off, n)` may be
+  called as soon as gflat[off:off+n] is final on the current stream; `finish()` reduces whatever was
+  not covered and makes the current stream wait for every piece."""
+
+  def __init__(self, gflat, group):
+    self.gflat, self.group, self.works, self.done = gflat, group, [], []
+
+  def reduce(self, off, n):
+    if n <= 0:
+      return
+    self.works.append(dist.all_reduce(self.gflat[off:off + n], op=dist.ReduceOp.SUM, group=self.group,
+                                      async_op=True))
+    self.done.append((off, n))
+
+  def finish(self):
+    pos = 0
+    for off, n in sorted(self.done) + [(self.gflat.numel(), 0)]:
+      if off < pos:
+        raise RuntimeError("GradReducer: overlapping pieces at offset %d" % off)
+      self.reduce(pos, off - pos)
+      pos = off + n
+    for w in self.works:
+      w.wait()
+    self.works = []
+
+
 class DPEncodeFn(torch.autograd.Function):
   """EncodeFn with the embedding all-gather inside (forward) and the gradient all-reduce
   (backward).  Returns GLOBAL-batch (vid, txt, tw)."""
@@ -66,11 +97,14 @@ class DPEncodeFn(torch.autograd.Function):
     engine.zero_small_grads(net.cfg, gflat)
     dtext_g = engine.head_backward(net.cfg, net.flat, gflat, sv_h, dtxt.contiguous(),
                                    dtw.contiguous(), need_dtext=ctx.needs_input_grad[1])
-    engine.video_backward(net.cfg, net.flat, gflat, sv_v,
-                          dvid[rank * bl:(rank + 1) * bl].contiguous())
+    red = GradReducer(gflat, group)
     for off, n in head_segments(net.layout):
       gflat[off:off + n].mul_(1.0 / w)
-    dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=group)
+      red.reduce(off, n)
+    layer_range = getattr(net.layout, "layer_big_range", None)
+    engine.video_backward(net.cfg, net.flat, gflat, sv_v, dvid[rank * bl:(rank + 1) * bl].contiguous(),
+                          on_layer_done=(lambda l: red.reduce(*layer_range(l))) if layer_range else None)
+    red.finish()
     net._publish_grads(gflat, accumulate)
     ctx.sv = None
     dtext = dtext_g[rank * rl:(rank + 1) * rl] if dtext_g is not None else None

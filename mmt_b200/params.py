@@ -114,6 +114,12 @@ class Layout:
   def off(self, name):
     return self.segments[name].offset
 
+  def layer_big_range(self, l):
+    """(offset, numel) of encoder layer l's weight matrices (Wq|Wk|Wv, Wo, W1, W2: one contiguous block)."""
+    p = "vid_bert.encoder.layer.%d." % l
+    first, last = self.segments[p + "attention.self.query.weight"], self.segments[p + "output.dense.weight"]
+    return first.offset, last.offset + last.numel - first.offset
+
   def view(self, flat, name):
     s = self.segments[name]
     return flat[s.offset:s.offset + s.numel].view(s.shape)

@@ -23,7 +23,9 @@ class _Seg:
 def _layout():
   segs = {"wv": _Seg(0, D_IN * M * D, False), "wt": _Seg(D_IN * M * D, TD * M * D, True),
           "wm": _Seg(D_IN * M * D + TD * M * D, TD * M, True)}
-  L = types.SimpleNamespace(segments=segs, numel=D_IN * M * D + TD * M * D + TD * M)
+  # "layer 0" = the video weights, so the early per-layer all-reduce path is exercised
+  L = types.SimpleNamespace(segments=segs, numel=D_IN * M * D + TD * M * D + TD * M,
+                            layer_big_range=lambda l: (0, D_IN * M * D))
   return L
 
 
@@ -79,11 +81,14 @@ class _StubEngine:
     return gt
 
   @staticmethod
-  def video_backward(cfg, flat, gflat, sv, dvid):
+  def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
     with torch.enable_grad():
       f = flat.detach().clone().requires_grad_(True)
       gf, = torch.autograd.grad(_video(f, sv), f, dvid)
-    gflat += gf
+    nv = D_IN * M * D                      # only the video weights: the head runs are already in flight
+    gflat[:nv] += gf[:nv]
+    if on_layer_done is not None:
+      on_layer_done(0)
 
 
 def _worker(rank, port, q):
