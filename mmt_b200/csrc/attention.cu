@@ -11,10 +11,16 @@
 //             the SAME buffer as an MN-major operand (swizzle-128B/32B-atom boxes)
 //   warp 1    MMA issuer: S = Q K^T (kind::tf32, M=128, N=KB, 16 k-steps, operands in smem), then
 //             O += P V (A = P from TMEM, B = V from smem, KB/8 k-steps)
-//   warps 2-5 softmax: one thread per query row; scale + additive mask, running max / sum, exp2,
-//             Philox dropout (identical keying to the unfused path), write P, rescale O if the
-//             running max moved; finally O / l -> ctx and log-sum-exp for the backward pass
+//   warps 2-9 softmax: TWO threads per query row (each TMEM lane quarter is served by two warps that
+//             take half of the key columns each; row max / sum are exchanged through shared memory):
+//             scale + additive mask, running max / sum, exp2, Philox dropout (16 random bits per
+//             element, identical keying to the unfused path), write P, rescale O if the running max
+//             moved; finally O / l -> ctx and log-sum-exp for the backward pass.
+//             The softmax is the long pole of a tile (~25 ALU instructions per score with dropout
+//             against 2 x 128 MMA flops), hence the second warp set and the cheaper random bits.
 // Shared memory: Q 64 KB + K|V 112 KB = 176 KB; TMEM: S/P 224 columns + O 128 columns.
+// Q and K arrive as four 32-column slices of dh on separate barriers, so the score MMAs start after
+// the first quarter of the operand bytes.
 #include "tc_ptx.cuh"
 
 namespace mmt {
@@ -24,7 +30,8 @@ using namespace tc;
 constexpr int DH = 128;                 // head dim (4 sub-tiles of 32 fp32 = 128 B rows)
 constexpr int QM = 128;                 // query rows per CTA
 constexpr int KB = 224;                 // keys per block (UMMA N, multiple of 16, <= 256)
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;                // TMA warp, MMA warp, 8 softmax warps
+constexpr int SM_THREADS = 256;
 constexpr uint32_t Q_BYTES = QM * DH * 4;          // 64 KB
 constexpr uint32_t KV_BYTES = KB * DH * 4;         // 112 KB
 constexpr uint32_t TM_S = 0, TM_O = 256;           // TMEM column offsets (512 allocated)
@@ -38,15 +45,24 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
-        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]),
-        "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]),
-        "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -82,16 +98,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   uint8_t* sq = smem;                       // 4 sub-tiles [128 rows x 128 B]
   uint8_t* skv = smem + Q_BYTES;            // K: 4 sub-tiles [224 rows x 128 B];  V: 4 n-chunks [224 k-rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + KV_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* k_free = bars + 3;              // score MMAs have finished reading K
-  uint64_t* v_free = bars + 4;              // P V MMAs have finished reading V
-  uint64_t* s_full = bars + 5;              // scores ready in TMEM
-  uint64_t* p_full = bars + 6;              // probabilities written (and O rescaled) -- 128 arrivals
-  uint64_t* o_full = bars + 7;              // P V accumulated
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* qk_full = bars + 0;             // [4] Q and K sub-tile t (32 of the dh columns) have landed
+  uint64_t* v_full = bars + 4;
+  uint64_t* k_free = bars + 5;              // score MMAs have finished reading K
+  uint64_t* v_free = bars + 6;              // P V MMAs have finished reading V
+  uint64_t* s_full = bars + 7;              // scores ready in TMEM
+  uint64_t* p_full = bars + 8;              // probabilities written (and O rescaled) -- 256 arrivals
+  uint64_t* o_full = bars + 9;              // P V accumulated
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   float* smask = reinterpret_cast<float*>(bars + 16);      // additive mask of the current key block (log2 domain)
+  float* xch = smask + KB;                                 // [2][128] row max / row sum exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = args.H, S = args.S;
@@ -101,7 +117,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   const int d_model = H * DH;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], i == 6 ? 128 : 1);
+    for (int i = 0; i < 10; ++i) mbar_init(&bars[i], i == 8 ? SM_THREADS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
@@ -117,16 +133,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int row_q = b * S + q0;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) tma_load_2d(sq + t * (QM * 128), &map_q, q_full, h * DH + 32 * t, row_q);
       for (int j = 0; j < nblk; ++j) {
         const int row_k = b * S + j * KB;
         mbar_wait(v_free, (j & 1) ^ 1);                       // previous block's V no longer read
-        mbar_arrive_expect_tx(k_full, KV_BYTES);
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          tma_load_2d(skv + t * (KB * 128), &map_k, k_full, d_model + h * DH + 32 * t, row_k);
+        for (int t = 0; t < 4; ++t) {                          // per 32-column slice of dh: the MMAs start on slice 0
+          mbar_arrive_expect_tx(&qk_full[t], (j == 0 ? Q_BYTES / 4 : 0) + KV_BYTES / 4);
+          if (j == 0) tma_load_2d(sq + t * (QM * 128), &map_q, &qk_full[t], h * DH + 32 * t, row_q);
+          tma_load_2d(skv + t * (KB * 128), &map_k, &qk_full[t], d_model + h * DH + 32 * t, row_k);
+        }
         mbar_wait(k_free, j & 1);                             // scores done: K's buffer can take V
         mbar_arrive_expect_tx(v_full, KV_BYTES);
 #pragma unroll
@@ -142,13 +157,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_tf32(QM, KB, false, false);     // S[128 x KB] = Q K^T
       const uint32_t idesc_o = make_idesc_tf32(QM, DH, false, true);      // O[128 x dh] += P V (V MN-major)
-      mbar_wait(q_full, 0);
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(k_full, j & 1);
         if (j > 0) mbar_wait(o_full, (j - 1) & 1);            // S/P columns are free again
-        tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < DH / 8; ++ks) {
+          if ((ks & 3) == 0) { mbar_wait(&qk_full[ks >> 2], j & 1); tc_fence_after(); }
           const uint64_t da = make_smem_desc(smem_u32(sq) + (ks >> 2) * (QM * 128) + (ks & 3) * 32, 16, 1024, 2);
           const uint64_t db = make_smem_desc(smem_u32(skv) + (ks >> 2) * (KB * 128) + (ks & 3) * 32, 16, 1024, 2);
           umma_tf32(tmem + TM_S, da, db, idesc_s, ks > 0 ? 1u : 0u);
@@ -168,71 +181,81 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       }
     }
   } else {
-    // ===================== softmax / epilogue (warps 2..5) =====================
-    const int q = warp & 3;
+    // ===================== softmax / epilogue (warps 2..9) =====================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                          // which half of the key columns / of dh it handles
     const int r = q * 32 + lane;                               // query row within the tile == TMEM lane
     const int qi = q0 + r;
     const bool row_ok = qi < S;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int cbase = half * (KB / 2);                         // first key column of this thread's half
     const float* mrow = args.mask + (int64_t)b * S;
     const uint32_t prow = (uint32_t)(((int64_t)b * H + h) * S + qi);   // Philox row id (== unfused path)
     const uint64_t seed = args.seed + (args.ctr ? *args.ctr : 0);
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;                      // l_run: this half's share of the row sum
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * KB;
-      // additive mask terms of this key block, shared by the 128 softmax threads (named barrier 1)
-      for (int t = threadIdx.x - 64; t < KB; t += 128) {
+      // additive mask terms of this key block, shared by the softmax threads (named barrier 1)
+      for (int t = threadIdx.x - 64; t < KB; t += SM_THREADS) {
         const int key = key0 + t;
         smask[t] = key < S ? (1.0f - __ldg(mrow + key)) * args.mask_log2 : -INFINITY;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: block max of the masked, scaled scores (log2 domain)
-      float m_blk = -INFINITY;
+      // pass 1: block max of the masked, scaled scores (log2 domain) over this thread's columns
+      float m_part = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < KB / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+        float v[16];
+        tmem_ld16(tmem + TM_S + lane_addr + cbase + c * 16, v);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) m_blk = fmaxf(m_blk, fmaf(v[t], args.scale_log2, smask[c * 32 + t]));
+        for (int t = 0; t < 16; t += 4) {
+          const float4 mk = *reinterpret_cast<const float4*>(smask + cbase + c * 16 + t);
+          m_part = fmaxf(fmaxf(m_part, fmaf(v[t], args.scale_log2, mk.x)), fmaf(v[t + 1], args.scale_log2, mk.y));
+          m_part = fmaxf(fmaxf(m_part, fmaf(v[t + 2], args.scale_log2, mk.z)), fmaf(v[t + 3], args.scale_log2, mk.w));
+        }
       }
-      const float m_new = fmaxf(m_run, m_blk);
+      xch[half * QM + r] = m_part;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m_run, fmaxf(m_part, xch[(half ^ 1) * QM + r]));
       const float alpha = (j == 0) ? 0.f : fast_ex2(m_run - m_new);
       // pass 2: p = 2^(x - m_new), row sum (un-dropped), dropout, write P in place of S
       float l_blk = 0.f;
 #pragma unroll 1
       for (int c = 0; c < KB / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+        float v[16];
+        tmem_ld16(tmem + TM_S + lane_addr + cbase + c * 16, v);
 #pragma unroll
-        for (int t4 = 0; t4 < 32; t4 += 4) {
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        for (int t8 = 0; t8 < 16; t8 += 8) {
+          float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
           if (args.p_drop > 0.f)
-            sc = dropout_scale4(seed, args.site, prow, (uint32_t)((key0 + c * 32 + t4) >> 2), args.p_drop,
-                                args.inv_keep);
-          const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+            dropout_scale8_h16(seed, args.site, prow, (uint32_t)((key0 + cbase + c * 16 + t8) >> 3), args.p_drop,
+                               args.inv_keep, sc);
+          const float4 mk0 = *reinterpret_cast<const float4*>(smask + cbase + c * 16 + t8);
+          const float4 mk1 = *reinterpret_cast<const float4*>(smask + cbase + c * 16 + t8 + 4);
+          const float mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int t = t4 + u;
-            const float p = fast_ex2(fmaf(v[t], args.scale_log2, smask[c * 32 + t]) - m_new);   // 2^-inf = 0 past S
+          for (int u = 0; u < 8; ++u) {
+            const float p = fast_ex2(fmaf(v[t8 + u], args.scale_log2, mk[u]) - m_new);   // 2^-inf = 0 past S
             l_blk += p;
-            v[t] = p * scv[u];
+            v[t8 + u] = p * sc[u];
           }
         }
-        tmem_st32(tmem + TM_S + lane_addr + c * 32, v);
+        tmem_st16(tmem + TM_S + lane_addr + cbase + c * 16, v);
       }
-      // online-softmax rescale of the running accumulator (only when there was a previous block)
+      // online-softmax rescale of the running accumulator (only when there was a previous block):
+      // this thread's half of the dh columns
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);                        // previous P V has landed in O
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < DH / 32; ++c) {
-          float v[32];
-          tmem_ld32(tmem + TM_O + lane_addr + c * 32, v);
+          float v[16];
+          tmem_ld16(tmem + TM_O + lane_addr + half * (DH / 2) + c * 16, v);
 #pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] *= alpha;
-          tmem_st32(tmem + TM_O + lane_addr + c * 32, v);
+          for (int t = 0; t < 16; ++t) v[t] *= alpha;
+          tmem_st16(tmem + TM_O + lane_addr + half * (DH / 2) + c * 16, v);
         }
       }
       tmem_st_wait();
@@ -240,26 +263,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       m_run = m_new;
       tc_fence_before();
       mbar_arrive(p_full);
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // smask is rewritten by the next block
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // smask / xch are rewritten by the next block
     }
-    // epilogue: O / l -> ctx, log-sum-exp for backward
+    // epilogue: O / l -> ctx (this thread's half of dh), log-sum-exp for backward
+    xch[half * QM + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_run + xch[(half ^ 1) * QM + r];
     mbar_wait(o_full, (nblk - 1) & 1);
     tc_fence_after();
-    const float inv_l = args.out_scale / l_run;
-    float* orow = args.ctx + ((int64_t)b * S + qi) * d_model + h * DH;
+    const float inv_l = args.out_scale / l_tot;
+    float* orow = args.ctx + ((int64_t)b * S + qi) * d_model + h * DH + half * (DH / 2);
 #pragma unroll 1
     for (int c = 0; c < DH / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem + TM_O + lane_addr + c * 32, v);
+      float v[16];
+      tmem_ld16(tmem + TM_O + lane_addr + half * (DH / 2) + c * 16, v);
       if (row_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 4)
-          *reinterpret_cast<float4*>(orow + c * 32 + t) =
+        for (int t = 0; t < 16; t += 4)
+          *reinterpret_cast<float4*>(orow + c * 16 + t) =
               make_float4(v[t] * inv_l, v[t + 1] * inv_l, v[t + 2] * inv_l, v[t + 3] * inv_l);
       }
     }
-    if (row_ok && args.lse)
-      args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_run)) * 0.69314718055994530942f;
+    if (row_ok && half == 0 && args.lse)
+      args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_tot)) * 0.69314718055994530942f;
     tc_fence_before();
   }
   __syncthreads();
@@ -301,7 +327,7 @@ extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B,
   a.out_scale = tc::kTf32TruncComp;
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.seed = seed; a.site = site; a.ctr = g_step_ctr;
-  constexpr size_t smem = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 64;
+  constexpr size_t smem = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 2 * QM * 4 + 64;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -82,6 +82,34 @@ __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, u
   return o;
 }
 
+// Attention-probability dropout (the S x S matrices: by far the most dropout decisions of a step) spends
+// 16 random bits per element: one Philox call covers 8 consecutive key columns [col8*8, col8*8+8).
+// P(drop) = floor(p * 65536) / 65536 (p = 0.1 -> 0.09999).  Element order: x.lo x.hi y.lo y.hi z.lo z.hi w.lo w.hi.
+__device__ __forceinline__ void dropout_scale8_h16(uint64_t seed, uint32_t site, uint32_t row, uint32_t col8,
+                                                   float p, float inv_keep, float (&o)[8]) {
+  const uint4 r = Philox::gen(seed, row, col8, site, 0x6d6d7468u);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i] = (w[i] & 0xffffu) >= thr ? inv_keep : 0.f;
+    o[2 * i + 1] = (w[i] >> 16) >= thr ? inv_keep : 0.f;
+  }
+}
+// the same decisions for the 4 columns [col4*4, col4*4+4) (row-per-warp kernels, one float4 per lane)
+__device__ __forceinline__ float4 dropout_scale4_h16(uint64_t seed, uint32_t site, uint32_t row, uint32_t col4,
+                                                     float p, float inv_keep) {
+  const uint4 r = Philox::gen(seed, row, col4 >> 1, site, 0x6d6d7468u);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const uint32_t w0 = (col4 & 1) ? r.z : r.x, w1 = (col4 & 1) ? r.w : r.y;
+  float4 o;
+  o.x = (w0 & 0xffffu) >= thr ? inv_keep : 0.f;
+  o.y = (w0 >> 16) >= thr ? inv_keep : 0.f;
+  o.z = (w1 & 0xffffu) >= thr ? inv_keep : 0.f;
+  o.w = (w1 >> 16) >= thr ? inv_keep : 0.f;
+  return o;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   // model/bert.py:53: x * 0.5 * (1 + erf(x / sqrt(2)))
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
         F4_OP(p, x[c].x * inv, x[c].y * inv, x[c].z * inv, x[c].w * inv);
         *reinterpret_cast<float4*>(Psoft + r * ld + j) = p;
         if (p_drop > 0.f) {
-          float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
+          float4 sc = dropout_scale4_h16(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
           F4_OP(p, p.x * sc.x, p.y * sc.y, p.z * sc.z, p.w * sc.w);
           *reinterpret_cast<float4*>(Pdrop + r * ld + j) = p;
         }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_bwd_kernel(
         da[c] = *reinterpret_cast<const float4*>(dP + r * ld + j);
         a[c] = *reinterpret_cast<const float4*>(Psoft + r * ld + j);
         if (p_drop > 0.f) {
-          float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
+          float4 sc = dropout_scale4_h16(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
           F4_OP(da[c], da[c].x * sc.x, da[c].y * sc.y, da[c].z * sc.z, da[c].w * sc.w);
         }
         float* pa = reinterpret_cast<float*>(&a[c]);
