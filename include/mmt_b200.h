@@ -158,13 +158,18 @@ int mmt_softmax_mask_bwd(float* dP_inout, const float* Psoft, int32_t B, int32_t
  * Fused flash-style self-attention forward (model/bert.py:136-172) on tcgen05 tensor cores:
  *   ctx[b,i,h*dh:(h+1)*dh] = dropout(softmax(Q K^T * scale + (1 - mask[b,:]) * -10000)) V
  * qkv [B*S, 3*H*dh] holds Q | K | V column blocks (the fused QKV projection's output); scores and
- * probabilities stay in TMEM -- nothing of size S x S touches HBM.  lse [B,H,S] (may be NULL)
- * receives the log-sum-exp of the masked, scaled scores.  dh must be 128.  The dropout mask is
- * the same function of (seed, site, (b*H+h)*S+i, j/4) that mmt_softmax_mask_fwd uses.
+ * probabilities are formed in TMEM.  With probs == NULL (inference) nothing of size S x S touches
+ * HBM.  With probs != NULL (training, S <= 224) the normalised probabilities [B,H,S,ld_p] and, when
+ * p_drop > 0, their dropped copy probs_drop are additionally streamed out (write-only) for the
+ * backward pass -- what the reference's autograd keeps (bert.py:155-160) -- so that the backward
+ * repeats neither Q K^T nor the softmax.  lse [B,H,S] (may be NULL) receives the log-sum-exp of the
+ * masked, scaled scores.  dh must be 128.  The dropout mask is the same function of
+ * (seed, site, (b*H+h)*S+i, j/8) that mmt_softmax_mask_fwd uses (16 random bits per element).
  * ------------------------------------------------------------------------------------------- */
 int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B, int32_t H, int32_t S,
                       int32_t dh, float scale, float p_drop, uint64_t seed, uint32_t site,
-                      float* ctx, float* lse, void* stream);
+                      float* ctx, float* lse, float* probs, float* probs_drop, int32_t ld_p,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Expert read-out + L2 normalisation (model/model.py:583-587, 621-623):

@@ -66,6 +66,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -89,9 +98,16 @@ struct AttArgs {
 
 // map_qk: qkv viewed as [B*S rows, 3*H*DH cols], box {32 cols, rows<=256}, SWIZZLE_128B
 // map_v : same tensor, box {32 cols, 32 rows}, SWIZZLE_128B_ATOM_32B (MN-major B operand)
+// WRITE_P (training, S <= KB): the normalised probabilities P and their dropped copy Pd are ALSO
+// streamed to HBM (TMA stores from a per-warp staging tile) for the backward pass, which then needs
+// neither the Q K^T product nor the softmax again; the row sum is taken in an extra exp pass so that
+// what is written (and what feeds the P V product) is already normalised.
+template <bool WRITE_P>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                        const __grid_constant__ CUtensorMap map_k,
                                                                        const __grid_constant__ CUtensorMap map_v,
+                                                                       const __grid_constant__ CUtensorMap map_p,
+                                                                       const __grid_constant__ CUtensorMap map_pd,
                                                                        const AttArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,7 +123,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   uint64_t* o_full = bars + 9;              // P V accumulated
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   float* smask = reinterpret_cast<float*>(bars + 16);      // additive mask of the current key block (log2 domain)
-  float* xch = smask + KB;                                 // [2][128] row max / row sum exchange between column halves
+  float* xch = smask + KB;                                 // [2][2][128] row max / row sum exchange between column halves
+  float* pstage = xch + 4 * QM;                            // WRITE_P: per softmax warp, P and Pd tiles [32 rows][16 cols]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = args.H, S = args.S;
@@ -220,11 +237,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float m_new = fmaxf(m_run, fmaxf(m_part, xch[(half ^ 1) * QM + r]));
       const float alpha = (j == 0) ? 0.f : fast_ex2(m_run - m_new);
+      float norm2 = m_new;                                     // exponent offset of pass 2
+      if (WRITE_P) {
+        // pass 1.5 (single key block): the row sum at the final max, so that pass 2 emits normalised P
+        float l_part = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < KB / 32; ++c) {
+          float v[16];
+          tmem_ld16(tmem + TM_S + lane_addr + cbase + c * 16, v);
+#pragma unroll
+          for (int t = 0; t < 16; t += 4) {
+            const float4 mk = *reinterpret_cast<const float4*>(smask + cbase + c * 16 + t);
+            l_part += (fast_ex2(fmaf(v[t], args.scale_log2, mk.x) - m_new) + fast_ex2(fmaf(v[t + 1], args.scale_log2, mk.y) - m_new)) +
+                      (fast_ex2(fmaf(v[t + 2], args.scale_log2, mk.z) - m_new) + fast_ex2(fmaf(v[t + 3], args.scale_log2, mk.w) - m_new));
+          }
+        }
+        xch[(2 + half) * QM + r] = l_part;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        norm2 = m_new + log2f(l_part + xch[(2 + (half ^ 1)) * QM + r]);
+      }
+      float* stg_p = pstage + (warp - 2) * (2 * 32 * 16);      // this warp's P tile, Pd tile right behind it
       // pass 2: p = 2^(x - m_new), row sum (un-dropped), dropout, write P in place of S
       float l_blk = 0.f;
 #pragma unroll 1
       for (int c = 0; c < KB / 32; ++c) {
         float v[16];
+        float pv[WRITE_P ? 16 : 1];
         tmem_ld16(tmem + TM_S + lane_addr + cbase + c * 16, v);
 #pragma unroll
         for (int t8 = 0; t8 < 16; t8 += 8) {
@@ -237,12 +275,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
           const float mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const float p = fast_ex2(fmaf(v[t8 + u], args.scale_log2, mk[u]) - m_new);   // 2^-inf = 0 past S
+            const float p = fast_ex2(fmaf(v[t8 + u], args.scale_log2, mk[u]) - norm2);   // 2^-inf = 0 past S
             l_blk += p;
+            if constexpr (WRITE_P) pv[t8 + u] = p;
             v[t8 + u] = p * sc[u];
           }
         }
         tmem_st16(tmem + TM_S + lane_addr + cbase + c * 16, v);
+        if constexpr (WRITE_P) {
+          if (lane == 0) bulk_wait_read0();                    // the previous chunk's stores have read the staging tiles
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 16; t += 4) {
+            *reinterpret_cast<float4*>(stg_p + lane * 16 + t) = make_float4(pv[t], pv[t + 1], pv[t + 2], pv[t + 3]);
+            if (args.p_drop > 0.f)
+              *reinterpret_cast<float4*>(stg_p + 32 * 16 + lane * 16 + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int bh = b * H + h;
+            tma_store_3d(&map_p, stg_p, key0 + cbase + c * 16, q0 + q * 32, bh);
+            if (args.p_drop > 0.f) tma_store_3d(&map_pd, stg_p + 32 * 16, key0 + cbase + c * 16, q0 + q * 32, bh);
+            bulk_commit();
+          }
+        }
       }
       // online-softmax rescale of the running accumulator (only when there was a previous block):
       // this thread's half of the dh columns
@@ -260,7 +317,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       }
       tmem_st_wait();
       l_run = l_run * alpha + l_blk;
-      m_run = m_new;
+      m_run = WRITE_P ? norm2 : m_new;                         // WRITE_P: log2 of the full normaliser
       tc_fence_before();
       mbar_arrive(p_full);
       asm volatile("bar.sync 1, 256;" ::: "memory");          // smask / xch are rewritten by the next block
@@ -268,7 +325,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
     // epilogue: O / l -> ctx (this thread's half of dh), log-sum-exp for backward
     xch[half * QM + r] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float l_tot = l_run + xch[(half ^ 1) * QM + r];
+    const float l_tot = WRITE_P ? 1.0f : l_run + xch[(half ^ 1) * QM + r];    // WRITE_P: already normalised
     mbar_wait(o_full, (nblk - 1) & 1);
     tc_fence_after();
     const float inv_l = args.out_scale / l_tot;
@@ -285,7 +342,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
       }
     }
     if (row_ok && half == 0 && args.lse)
-      args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_tot)) * 0.69314718055994530942f;
+      args.lse[((int64_t)b * H + h) * S + qi] = (WRITE_P ? m_run : m_run + log2f(l_tot)) * 0.69314718055994530942f;
+    if (WRITE_P && lane == 0) bulk_wait0();                    // P / Pd stores complete before the CTA retires
     tc_fence_before();
   }
   __syncthreads();
@@ -299,6 +357,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
 
 int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                     int box_rows, bool atom32, const char* what);
+int make_f32_store_map3d(CUtensorMap* map, float* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
+                         int64_t batch_stride, int box_cols, int box_rows, const char* what);
 
 }  // namespace mmt
 
@@ -306,19 +366,36 @@ using namespace mmt;
 
 extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B, int32_t H, int32_t S,
                                  int32_t dh, float scale, float p_drop, uint64_t seed, uint32_t site,
-                                 float* ctx, float* lse, void* stream) {
+                                 float* ctx, float* lse, float* probs, float* probs_drop, int32_t ld_p,
+                                 void* stream) {
   MMT_ARG_CHECK(qkv && mask && ctx, MMT_E_ARG, "mmt_attention_fwd: null pointer");
   MMT_ARG_CHECK(dh == DH, MMT_E_SHAPE, "mmt_attention_fwd: head dim %d unsupported (only %d)", dh, DH);
   MMT_ARG_CHECK(B > 0 && H > 0 && S > 0 && B <= 65535 && H <= 65535, MMT_E_SHAPE, "mmt_attention_fwd: bad shape B=%d H=%d S=%d", B, H, S);
   MMT_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f, MMT_E_ARG, "mmt_attention_fwd: p_drop=%f", (double)p_drop);
+  const bool write_p = probs != nullptr;
+  if (write_p) {
+    MMT_ARG_CHECK(S <= KB, MMT_E_UNSUPPORTED, "mmt_attention_fwd: probabilities can be saved for S <= %d only (S=%d)", KB, S);
+    MMT_ARG_CHECK(ld_p >= S && (ld_p & 3) == 0, MMT_E_SHAPE, "mmt_attention_fwd: ld_p=%d (S=%d)", ld_p, S);
+    MMT_ARG_CHECK(p_drop == 0.f || probs_drop != nullptr, MMT_E_ARG, "mmt_attention_fwd: probs_drop missing");
+  }
   const int64_t rows = (int64_t)B * S, cols = 3LL * H * DH;
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mp, mpd;
   int rc = make_tf32_map2d(&mq, qkv, rows, cols, cols, 32, QM, false, "Q");
   if (rc) return rc;
   rc = make_tf32_map2d(&mk, qkv, rows, cols, cols, 32, KB, false, "K");
   if (rc) return rc;
   rc = make_tf32_map2d(&mv, qkv, rows, cols, cols, 32, 32, true, "V");
   if (rc) return rc;
+  mp = mq; mpd = mq;                                           // placeholders when nothing is saved
+  if (write_p) {
+    rc = make_f32_store_map3d(&mp, probs, ld_p, S, (int64_t)B * H, ld_p, (int64_t)S * ld_p, 16, 32, "P");
+    if (rc) return rc;
+    mpd = mp;
+    if (p_drop > 0.f) {
+      rc = make_f32_store_map3d(&mpd, probs_drop, ld_p, S, (int64_t)B * H, ld_p, (int64_t)S * ld_p, 16, 32, "Pd");
+      if (rc) return rc;
+    }
+  }
   AttArgs a;
   a.mask = mask; a.ctx = ctx; a.lse = lse;
   a.B = B; a.H = H; a.S = S;
@@ -327,15 +404,21 @@ extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B,
   a.out_scale = tc::kTf32TruncComp;
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.seed = seed; a.site = site; a.ctr = g_step_ctr;
-  constexpr size_t smem = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 2 * QM * 4 + 64;
+  constexpr size_t smem_base = Q_BYTES + KV_BYTES + 1024 + 128 + KB * 4 + 4 * QM * 4;
+  constexpr size_t smem_save = smem_base + 8 * 2 * 32 * 16 * 4;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_base);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_save);
     if (e != cudaSuccess) return cuda_status(e, "attention_fwd smem attribute");
     configured = true;
   }
   dim3 grid((S + QM - 1) / QM, H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, smem, (cudaStream_t)stream>>>(mq, mk, mv, a);
+  if (write_p)
+    attention_fwd_kernel<true><<<grid, ATT_THREADS, smem_save, (cudaStream_t)stream>>>(mq, mk, mv, mp, mpd, a);
+  else
+    attention_fwd_kernel<false><<<grid, ATT_THREADS, smem_base, (cudaStream_t)stream>>>(mq, mk, mv, mp, mpd, a);
   MMT_LAUNCH_CHECK("attention_fwd_kernel");
   return 0;
 }

@@ -333,6 +333,23 @@ int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t c
   return 0;
 }
 
+// Un-swizzled 3-D fp32 tensor map [batches, rows, cols] for TMA stores from a dense [box_rows][box_cols] tile.
+int make_f32_store_map3d(CUtensorMap* map, float* base, int64_t cols, int64_t rows, int64_t batches, int64_t ld,
+                         int64_t batch_stride, int box_cols, int box_rows, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0 && (batch_stride * 4) % 16 == 0, MMT_E_ALIGN,
+                "tensor map %s needs a 16-byte aligned base and pitches", what);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
 int gemm_tc_persistent(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
 int gemm_tc_pair(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken);
 

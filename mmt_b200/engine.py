@@ -5,6 +5,7 @@ kernel in libmmt_b200.so; PyTorch only allocates the buffers.  Reference semanti
 cited at each stage; the math is restated in oracle/mmt_oracle.py and SURVEY.md Appendix A.
 """
 import math
+import os
 
 import torch
 
@@ -46,6 +47,9 @@ class Config:
     # flash-style fused attention forward (scores / probabilities never leave TMEM); the backward
     # pass recomputes the probabilities.  Needs the tf32 attention path and dh == 128.
     self.fused_attention = True
+    # training: the fused forward also streams P / dropout(P) out for the backward pass (S <= 224);
+    # False = keep nothing of size S x S and recompute Q K^T + softmax in the backward instead
+    self.save_attention_probs = os.environ.get("MMT_SAVE_PROBS", "1") != "0"
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -171,8 +175,13 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
     if fused:
       # K5 fused: softmax(Q K^T / sqrt(dh) + mask) V in one tcgen05 kernel (bert.py:147-170)
       P = Pd = None
+      if training and cfg.save_attention_probs and S <= 224:
+        P = _empty((B, H, S, Sp), flat)
+        Pd = _empty((B, H, S, Sp), flat) if p_att > 0 else P
       check(lib.mmt_attention_fwd(ptr(qkv), ptr(sv.mask), B, H, S, dh, scale, p_att, seed,
-                                  SITE_LAYER + 4 * l, ptr(ctx), None, st), "mmt_attention_fwd")
+                                  SITE_LAYER + 4 * l, ptr(ctx), None, ptr(P) if P is not None else None,
+                                  ptr(Pd) if (P is not None and p_att > 0) else None, Sp, st),
+            "mmt_attention_fwd")
     else:
       P, Pd = _attention_probs(cfg, lib, st, qkv, sv.mask, B, H, S, Sp, d, dh, scale, p_att, seed,
                                SITE_LAYER + 4 * l, aprec)

@@ -606,7 +606,7 @@ def test_fused_attention_forward_matches_reference(dev, Bt, S):
   ctx = torch.full((Bt * S, d), float("nan"), device=dev)
   lse = torch.empty(Bt, Hh, S, device=dev)
   _lib.check(lib.mmt_attention_fwd(_lib.ptr(qd), _lib.ptr(md), Bt, Hh, S, dh, 1 / math.sqrt(dh), 0.0, 0, 0,
-                                   _lib.ptr(ctx), _lib.ptr(lse), _lib.stream_ptr()), "attention_fwd")
+                                   _lib.ptr(ctx), _lib.ptr(lse), None, None, 0, _lib.stream_ptr()), "attention_fwd")
   torch.cuda.synchronize()
   e_ctx, e_lse = H.rel_err(ctx, ref), float((lse.cpu().double() - lse_ref).abs().max())
   print("fused attention S=%d: ctx rel err %.2e, lse abs err %.2e" % (S, e_ctx, e_lse))
@@ -628,7 +628,7 @@ def test_fused_attention_dropout_matches_unfused_path(dev):
   scale, p, seed, site = 1 / math.sqrt(dh), 0.1, 1234567, 20
   ctx = torch.empty(Bt * S, d, device=dev)
   _lib.check(lib.mmt_attention_fwd(_lib.ptr(qkv), _lib.ptr(mask), Bt, Hh, S, dh, scale, p, seed, site,
-                                   _lib.ptr(ctx), None, _lib.stream_ptr()), "attention_fwd")
+                                   _lib.ptr(ctx), None, None, None, 0, _lib.stream_ptr()), "attention_fwd")
   P = torch.empty(Bt, Hh, S, Sp, device=dev)
   _lib.gemm(S, S, dh, qkv, 3 * d, 1, qkv, 3 * d, 1, P, Sp, b_off=d, batch=Bt * Hh, batch_inner=Hh,
             a_bs=(S * 3 * d, dh), b_bs=(S * 3 * d, dh), c_bs=(Hh * S * Sp, S * Sp))
@@ -639,6 +639,44 @@ def test_fused_attention_dropout_matches_unfused_path(dev):
   _lib.gemm(S, dh, S, Pd, Sp, 1, qkv, 1, 3 * d, ctx2, d, b_off=2 * d, batch=Bt * Hh, batch_inner=Hh,
             a_bs=(Hh * S * Sp, S * Sp), b_bs=(S * 3 * d, dh), c_bs=(S * d, dh))
   assert H.rel_err(ctx, ctx2) < 2e-3
+  # training mode of the fused kernel: P and dropout(P) streamed out for the backward pass must be the
+  # materialised path's matrices (same dropout decisions, entry for entry), ctx and lse unchanged
+  for S2, p2 in ((218, 0.1), (218, 0.0), (31, 0.1), (224, 0.1)):
+    Sp2 = (S2 + 3) // 4 * 4
+    g2 = torch.Generator().manual_seed(S2)
+    qkv2 = torch.randn(Bt * S2, 3 * d, generator=g2).to(dev)
+    mask2 = (torch.rand(Bt, S2, generator=g2) > 0.3).float()
+    mask2[:, 0] = 1
+    mask2 = mask2.to(dev)
+    Pm = torch.empty(Bt, Hh, S2, Sp2, device=dev)
+    _lib.gemm(S2, S2, dh, qkv2, 3 * d, 1, qkv2, 3 * d, 1, Pm, Sp2, b_off=d, batch=Bt * Hh, batch_inner=Hh,
+              a_bs=(S2 * 3 * d, dh), b_bs=(S2 * 3 * d, dh), c_bs=(Hh * S2 * Sp2, S2 * Sp2),
+              precision=_lib.PREC_TF32)
+    Pdm = torch.empty_like(Pm) if p2 > 0 else Pm
+    _lib.check(lib.mmt_softmax_mask_fwd(_lib.ptr(Pm), _lib.ptr(mask2), Bt, Hh, S2, Sp2, scale, p2, seed, site,
+                                        _lib.ptr(Pm), _lib.ptr(Pdm) if p2 > 0 else None, _lib.stream_ptr()),
+               "softmax")
+    ctx_a = torch.empty(Bt * S2, d, device=dev)
+    ctx_b = torch.empty(Bt * S2, d, device=dev)
+    lse_a, lse_b = torch.empty(Bt, Hh, S2, device=dev), torch.empty(Bt, Hh, S2, device=dev)
+    Pf = torch.full((Bt, Hh, S2, Sp2), float("nan"), device=dev)
+    Pdf = torch.full((Bt, Hh, S2, Sp2), float("nan"), device=dev) if p2 > 0 else Pf
+    _lib.check(lib.mmt_attention_fwd(_lib.ptr(qkv2), _lib.ptr(mask2), Bt, Hh, S2, dh, scale, p2, seed, site,
+                                     _lib.ptr(ctx_a), _lib.ptr(lse_a), None, None, 0, _lib.stream_ptr()), "attention_fwd")
+    _lib.check(lib.mmt_attention_fwd(_lib.ptr(qkv2), _lib.ptr(mask2), Bt, Hh, S2, dh, scale, p2, seed, site,
+                                     _lib.ptr(ctx_b), _lib.ptr(lse_b), _lib.ptr(Pf),
+                                     _lib.ptr(Pdf) if p2 > 0 else None, Sp2, _lib.stream_ptr()), "attention_fwd")
+    torch.cuda.synchronize()
+    assert torch.isfinite(Pf[..., :S2]).all() and torch.isfinite(Pdf[..., :S2]).all()
+    eP = float((Pf[..., :S2] - Pm[..., :S2]).abs().max())
+    ePd = float((Pdf[..., :S2] - Pdm[..., :S2]).abs().max())
+    same_mask = bool(((Pdf[..., :S2] == 0) == (Pdm[..., :S2] == 0)).all())
+    print("saved probabilities S=%d p=%.1f: |dP| %.2e |dPd| %.2e ctx %.2e lse %.2e" %
+          (S2, p2, eP, ePd, H.rel_err(ctx_b, ctx_a), float((lse_a - lse_b).abs().max())))
+    assert eP < 2e-4 and ePd < 3e-4 and same_mask
+    # ctx: the P V product sees normalised instead of un-normalised probabilities, i.e. different tf32
+    # truncations of its A operand -- same accuracy class, not bit-identical
+    assert H.rel_err(ctx_b, ctx_a) < 1e-3 and float((lse_a - lse_b).abs().max()) < 1e-4
 
 
 def test_graphed_train_step_matches_eager_and_draws_fresh_dropout(dev):
