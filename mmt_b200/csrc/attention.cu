@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap map_p,
                                                                        const __grid_constant__ CUtensorMap map_pd,
                                                                        const AttArgs args) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sq = smem;                       // 4 sub-tiles [128 rows x 128 B]
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_fwd_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                           // prologue done: now wait for the producer grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -416,9 +418,9 @@ extern "C" int mmt_attention_fwd(const float* qkv, const float* mask, int32_t B,
   }
   dim3 grid((S + QM - 1) / QM, H, B);
   if (write_p)
-    attention_fwd_kernel<true><<<grid, ATT_THREADS, smem_save, (cudaStream_t)stream>>>(mq, mk, mv, mp, mpd, a);
+    launch_pdl(attention_fwd_kernel<true>, dim3(grid), dim3(ATT_THREADS), smem_save, (cudaStream_t)stream, mq, mk, mv, mp, mpd, a);
   else
-    attention_fwd_kernel<false><<<grid, ATT_THREADS, smem_base, (cudaStream_t)stream>>>(mq, mk, mv, mp, mpd, a);
+    launch_pdl(attention_fwd_kernel<false>, dim3(grid), dim3(ATT_THREADS), smem_base, (cudaStream_t)stream, mq, mk, mv, mp, mpd, a);
   MMT_LAUNCH_CHECK("attention_fwd_kernel");
   return 0;
 }

@@ -1,5 +1,6 @@
 // Shared device/host helpers for the mmt_b200 sm_100a kernels.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -66,6 +67,37 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// Every kernel of this library starts with pdl_trigger() (the next kernel in the stream may begin
+// launching: its CTAs take SMs as this grid's CTAs retire and run their prologue -- barrier init,
+// TMEM allocation, descriptor prefetch) and calls pdl_wait() before its first access to global
+// memory (returns once the preceding grid has completed and its writes are visible).  A train step
+// is ~150 dependent launches; the launch / drain gap between two of them is a few microseconds.
+// Both instructions are no-ops for a kernel launched without the attribute (MMT_PDL=0).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MMT_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // keep-mask scale for 4 consecutive columns [col4*4, col4*4+4) of `row` at dropout `site`.
 // Returns 0 or 1/(1-p) per element.  p == 0 -> all ones (callers skip the call).

@@ -34,6 +34,8 @@ __device__ __forceinline__ int64_t c_off(const mmt_gemm_desc& d, int m) {
 // A_KFAST: consecutive threads walk k (operand contiguous along k); else they walk m / n.
 template <bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmArgs args) {
+  pdl_trigger();
+  pdl_wait();
   const mmt_gemm_desc& d = args.d;
   __shared__ float As[2][BK][BM + PAD];
   __shared__ float Bs[2][BK][BN + PAD];
@@ -153,6 +155,8 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmArgs args) {
 // shapes is pure latency.  One thread = 2 x 2 outputs; fp32 FMAs in k order.
 constexpr int SB = 32;
 __global__ void __launch_bounds__(NT) sgemm_small_kernel(const GemmArgs args) {
+  pdl_trigger();
+  pdl_wait();
   const mmt_gemm_desc& d = args.d;
   __shared__ float As[BK][SB + 1];
   __shared__ float Bs[BK][SB + 1];
@@ -213,7 +217,7 @@ int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
   if (d.M <= 96 && d.N <= 96) {                     // small outputs: 32 x 32 tiles
     GemmArgs small{d, 1, 0};
     dim3 g((d.N + SB - 1) / SB, (d.M + SB - 1) / SB, d.batch);
-    sgemm_small_kernel<<<g, NT, 0, stream>>>(small);
+    launch_pdl(sgemm_small_kernel, dim3(g), dim3(NT), 0, stream, small);
     MMT_LAUNCH_CHECK("sgemm_small_kernel");
     return 0;
   }
@@ -235,10 +239,10 @@ int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
   dim3 grid((d.N + BN - 1) / BN, (d.M + BM - 1) / BM, d.batch * args.split_k);
   const bool a_kfast = (d.a_ks == 1);
   const bool b_kfast = (d.b_ks == 1);
-  if (a_kfast && b_kfast) sgemm_kernel<true, true><<<grid, NT, 0, stream>>>(args);
-  else if (a_kfast) sgemm_kernel<true, false><<<grid, NT, 0, stream>>>(args);
-  else if (b_kfast) sgemm_kernel<false, true><<<grid, NT, 0, stream>>>(args);
-  else sgemm_kernel<false, false><<<grid, NT, 0, stream>>>(args);
+  if (a_kfast && b_kfast) launch_pdl(sgemm_kernel<true, true>, dim3(grid), dim3(NT), 0, stream, args);
+  else if (a_kfast) launch_pdl(sgemm_kernel<true, false>, dim3(grid), dim3(NT), 0, stream, args);
+  else if (b_kfast) launch_pdl(sgemm_kernel<false, true>, dim3(grid), dim3(NT), 0, stream, args);
+  else launch_pdl(sgemm_kernel<false, false>, dim3(grid), dim3(NT), 0, stream, args);
   MMT_LAUNCH_CHECK("sgemm_kernel");
   return 0;
 }

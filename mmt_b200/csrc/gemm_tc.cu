@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   constexpr uint32_t A_BYTES = BM * BK * 4;     // 16 KB
   constexpr uint32_t B_BYTES = BN * BK * 4;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is only 16 B aligned by contract
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();                                           // prologue done: now wait for the producer grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -278,7 +280,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& args, cud
     configured = true;
   }
   dim3 grid((args.d.N + BN - 1) / BN, (args.d.M + BM - 1) / BM, args.split_k * args.d.batch);
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
+  launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, ma, mb, args);
   MMT_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
                                                                   const Tc2Args args) {
   constexpr int STAGES = BN == 256 ? 4 : 6;
   constexpr uint32_t B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // prologue done: now wait for the producer grid
 
   // work item -> (batch z, m0, n0, k-block range)
   auto decode = [&](int w, int& z, int& m0, int& n0, int& kb0, int& nkb) {
@@ -282,7 +284,7 @@ int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, c
   }
   const int work = args.num_m_tiles * args.num_n_tiles * args.split_k * args.d.batch;
   const int grid = work < num_sms() ? work : num_sms();
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, args);
+  launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, ma, mb, args);
   MMT_LAUNCH_CHECK("gemm_tc2_kernel");
   return 0;
 }

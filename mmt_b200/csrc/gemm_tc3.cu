@@ -110,6 +110,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
@@ -137,6 +138,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();                                   // peer barriers initialised, TMEM allocated in both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                           // prologue done: now wait for the producer grid
 
   // work item -> (batch z, m0, n0, k-block range)
   auto decode = [&](int w, int& z, int& m0, int& n0, int& kb0, int& nkb) {
@@ -366,7 +368,7 @@ int launch3(const CUtensorMap& ma, const CUtensorMap& mb, const Tc3Args& args, c
   const int work = args.num_m_tiles * args.num_n_tiles * args.split_k;
   const int max_pairs = num_sms() / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
-  kern<<<2 * pairs, NUM_THREADS, smem, stream>>>(ma, mb, args);          // __cluster_dims__(2,1,1)
+  launch_pdl(kern, dim3(2 * pairs), dim3(NUM_THREADS), smem, stream, ma, mb, args);          // __cluster_dims__(2,1,1)
   MMT_LAUNCH_CHECK("gemm_tc3_kernel");
   return 0;
 }

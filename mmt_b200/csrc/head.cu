@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
                                                        float* __restrict__ run_var,
                                                        float* __restrict__ mean_o,
                                                        float* __restrict__ rstd_o) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int ty = threadIdx.y;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(WARPS * 32) geu_gate_fwd_kernel(
     const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
     const float* __restrict__ bn_rstd, int R, int M, float* __restrict__ E, float* __restrict__ Y,
     float* __restrict__ inv_n1, float* __restrict__ inv_n2) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(WARPS * 32) geu_gate_bwd_rows_kernel(
     const float* __restrict__ bn_rstd, const float* __restrict__ inv_n1,
     const float* __restrict__ inv_n2, int R, int M, float* __restrict__ dX,
     float* __restrict__ dGhat) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(float* __restrict__ dG,
                                                      const float* __restrict__ bn_rstd, int R, int C,
                                                      int training, float* __restrict__ dbn_w,
                                                      float* __restrict__ dbn_b) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red1[8][33], red2[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int ty = threadIdx.y;
@@ -223,6 +231,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(float* __restrict__ dG,
 // ------------------------------------------------------------------------------------------
 __global__ void moe_softmax_fwd_kernel(const float* __restrict__ logits, int R, int M, int ld,
                                        float* __restrict__ w) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.y + threadIdx.y;
   if (r >= R) return;
   const int lane = threadIdx.x;
@@ -236,6 +246,8 @@ __global__ void moe_softmax_fwd_kernel(const float* __restrict__ logits, int R, 
 
 __global__ void moe_softmax_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ w,
                                        int R, int M, int ld, float* __restrict__ dlogits) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * blockDim.y + threadIdx.y;
   if (r >= R) return;
   const int lane = threadIdx.x;
@@ -259,6 +271,8 @@ __global__ void __launch_bounds__(256) sims_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ vw, int Nq, int Nv,
                                                        int M, int caps, int merge_avg,
                                                        float* __restrict__ sims) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int io = blockIdx.y;                               // output row
   if (j >= Nv) return;
@@ -289,6 +303,8 @@ __global__ void __launch_bounds__(256) sims_bwd_kernel(const float* __restrict__
                                                        int M, int caps, int merge_avg,
                                                        float* __restrict__ ddots,
                                                        float* __restrict__ dtw) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][MAXM];
   const int i = blockIdx.x;
   const int io = merge_avg ? i / caps : i;
@@ -342,6 +358,8 @@ __global__ void __launch_bounds__(256) sims_bwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) max_margin_fwd_kernel(const float* __restrict__ x, int n,
                                                              int rows_per_block, float margin,
                                                              float* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = 4 * (blockIdx.x * 256 + threadIdx.x);           // n % 4 == 0 guaranteed by the host
@@ -403,6 +421,8 @@ __global__ void __launch_bounds__(256) max_margin_kernel(const float* __restrict
   const int i_end = min(n, i_begin + rows_per_block);
   constexpr int RU = 4;                          // rows in flight per thread (memory-level parallelism)
   for (int ib = i_begin; ib < i_end; ib += RU) {
+  pdl_trigger();
+  pdl_wait();
     float dii[RU];
     float4 xr[RU];
 #pragma unroll
@@ -471,6 +491,8 @@ __global__ void __launch_bounds__(256) max_margin_kernel(const float* __restrict
 __global__ void max_margin_finish_kernel(int n, float inv_cnt, int fix_norm, float diag_correction,
                                          const float* __restrict__ ws, float* __restrict__ loss,
                                          float* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *loss = (n > 1 || !fix_norm) ? (ws[0] - diag_correction) * inv_cnt : __int_as_float(0x7fc00000);
   // fix_norm == 0: the diagonal terms relu(margin) are constants w.r.t. x (x_ii cancels) -> the
@@ -486,6 +508,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    int64_t n4, int64_t n, float lr, float b1, float b2,
                                                    float eps, float wd, int step, const uint64_t* __restrict__ ctr,
                                                    float gscale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {
     const float t = (float)(step + (ctr ? (int)*ctr : 0));      // device-side step counter for graph replays
@@ -539,11 +563,11 @@ int mmt_geu_gate_fwd(const float* X, const float* G, const float* bn_w, const fl
   MMT_ARG_CHECK(R > 0 && M > 0, MMT_E_SHAPE, "mmt_geu_gate_fwd: bad shape R=%d M=%d", R, M);
   CHECK_D(d);
   const int C = M * d;
-  bn_stats_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  launch_pdl(bn_stats_kernel, dim3((C + 31) / 32), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, 
       G, R, C, training, momentum, bn_eps, run_mean, run_var, bn_mean, bn_rstd);
   MMT_LAUNCH_CHECK("bn_stats");
   const int64_t rows = (int64_t)R * M;
-  DISPATCH_VEC(d, (geu_gate_fwd_kernel<V><<<(int)((rows + WARPS - 1) / WARPS), WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(geu_gate_fwd_kernel<V>, dim3((int)((rows + WARPS - 1) / WARPS)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       X, G, bn_w, bn_b, bn_mean, bn_rstd, R, M, E, Y, inv_n1, inv_n2)));
   MMT_LAUNCH_CHECK("geu_gate_fwd");
   return 0;
@@ -558,11 +582,11 @@ int mmt_geu_gate_bwd(const float* dE, const float* X, const float* G, const floa
                 dX && dG && dbn_w && dbn_b, MMT_E_ARG, "mmt_geu_gate_bwd: null pointer");
   CHECK_D(d);
   const int64_t rows = (int64_t)R * M;
-  DISPATCH_VEC(d, (geu_gate_bwd_rows_kernel<V><<<(int)((rows + WARPS - 1) / WARPS), WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(geu_gate_bwd_rows_kernel<V>, dim3((int)((rows + WARPS - 1) / WARPS)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       dE, X, G, Y, E, bn_w, bn_b, bn_mean, bn_rstd, inv_n1, inv_n2, R, M, dX, dG)));
   MMT_LAUNCH_CHECK("geu_gate_bwd_rows");
   const int C = M * d;
-  bn_bwd_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(dG, G, bn_w, bn_mean, bn_rstd, R, C, training, dbn_w, dbn_b);
+  launch_pdl(bn_bwd_kernel, dim3((C + 31) / 32), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, dG, G, bn_w, bn_mean, bn_rstd, R, C, training, dbn_w, dbn_b);
   MMT_LAUNCH_CHECK("bn_bwd");
   return 0;
 }
@@ -570,7 +594,7 @@ int mmt_geu_gate_bwd(const float* dE, const float* X, const float* G, const floa
 int mmt_moe_softmax_fwd(const float* logits, int32_t R, int32_t M, int32_t ld, float* w, void* stream) {
   MMT_ARG_CHECK(logits && w, MMT_E_ARG, "mmt_moe_softmax_fwd: null pointer");
   MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0 && ld >= M && ld <= 32, MMT_E_SHAPE, "mmt_moe_softmax_fwd: M=%d ld=%d must satisfy 1 <= M <= ld <= 32", M, ld);
-  moe_softmax_fwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(logits, R, M, ld, w);
+  launch_pdl(moe_softmax_fwd_kernel, dim3((R + 7) / 8), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, logits, R, M, ld, w);
   MMT_LAUNCH_CHECK("moe_softmax_fwd");
   return 0;
 }
@@ -579,7 +603,7 @@ int mmt_moe_softmax_bwd(const float* dw, const float* w, int32_t R, int32_t M, i
                         float* dlogits, void* stream) {
   MMT_ARG_CHECK(dw && w && dlogits, MMT_E_ARG, "mmt_moe_softmax_bwd: null pointer");
   MMT_ARG_CHECK(M >= 1 && M <= 32 && R > 0 && ld >= M && ld <= 32, MMT_E_SHAPE, "mmt_moe_softmax_bwd: M=%d ld=%d must satisfy 1 <= M <= ld <= 32", M, ld);
-  moe_softmax_bwd_kernel<<<(R + 7) / 8, dim3(32, 8), 0, (cudaStream_t)stream>>>(dw, w, R, M, ld, dlogits);
+  launch_pdl(moe_softmax_bwd_kernel, dim3((R + 7) / 8), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, dw, w, R, M, ld, dlogits);
   MMT_LAUNCH_CHECK("moe_softmax_bwd");
   return 0;
 }
@@ -593,7 +617,7 @@ int mmt_sims_combine_fwd(const float* dots, const float* tw, const float* vw, in
   const int rows_out = merge_avg ? Nv : Nq;
   dim3 grid((Nv + 255) / 256, rows_out);
   MMT_ARG_CHECK(rows_out <= 65535, MMT_E_SHAPE, "mmt_sims_combine_fwd: %d output rows > 65535 (chunk the queries)", rows_out);
-  sims_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dots, tw, vw, Nq, Nv, M, caps, merge_avg, sims);
+  launch_pdl(sims_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dots, tw, vw, Nq, Nv, M, caps, merge_avg, sims);
   MMT_LAUNCH_CHECK("sims_fwd");
   return 0;
 }
@@ -604,7 +628,7 @@ int mmt_sims_combine_bwd(const float* dsims, const float* dots, const float* tw,
   MMT_ARG_CHECK(dsims && dots && tw && vw && ddots && dtw, MMT_E_ARG, "mmt_sims_combine_bwd: null pointer");
   MMT_ARG_CHECK(M >= 1 && M <= MAXM && caps >= 1 && Nq == Nv * caps && Nv > 0, MMT_E_SHAPE,
                 "mmt_sims_combine_bwd: bad shape Nq=%d Nv=%d M=%d caps=%d", Nq, Nv, M, caps);
-  sims_bwd_kernel<<<Nq, 256, 0, (cudaStream_t)stream>>>(dsims, dots, tw, vw, Nq, Nv, M, caps, merge_avg, ddots, dtw);
+  launch_pdl(sims_bwd_kernel, dim3(Nq), dim3(256), 0, (cudaStream_t)stream, dsims, dots, tw, vw, Nq, Nv, M, caps, merge_avg, ddots, dtw);
   MMT_LAUNCH_CHECK("sims_bwd");
   return 0;
 }
@@ -626,13 +650,13 @@ int mmt_max_margin_fwd_bwd(const float* x, int32_t n, float margin, int32_t fix_
   float diag_correction = 0.f;
   if (dx == nullptr && n % 4 == 0 && ((uintptr_t)x % 16) == 0) {
     // forward only: uniform streaming loop; the n diagonal elements each contributed 2 relu(margin)
-    max_margin_fwd_kernel<<<dim3(chunks, strips), 256, 0, (cudaStream_t)stream>>>(x, n, rows_per_block, margin, workspace);
+    launch_pdl(max_margin_fwd_kernel, dim3(dim3(chunks, strips)), dim3(256), 0, (cudaStream_t)stream, x, n, rows_per_block, margin, workspace);
     if (fix_norm) diag_correction = 2.f * n * (margin > 0.f ? margin : 0.f);
   } else {
-    max_margin_kernel<<<dim3(chunks, strips), 256, 0, (cudaStream_t)stream>>>(x, n, rows_per_block, margin, fix_norm, inv_cnt, dx, workspace);
+    launch_pdl(max_margin_kernel, dim3(dim3(chunks, strips)), dim3(256), 0, (cudaStream_t)stream, x, n, rows_per_block, margin, fix_norm, inv_cnt, dx, workspace);
   }
   MMT_LAUNCH_CHECK("max_margin");
-  max_margin_finish_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, inv_cnt, fix_norm, diag_correction, workspace, loss, dx);
+  launch_pdl(max_margin_finish_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, n, inv_cnt, fix_norm, diag_correction, workspace, loss, dx);
   MMT_LAUNCH_CHECK("max_margin_finish");
   return 0;
 }
@@ -649,7 +673,7 @@ int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale);
+  launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale);
   MMT_LAUNCH_CHECK("adam");
   return 0;
 }

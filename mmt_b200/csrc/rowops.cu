@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
     uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ h, float* __restrict__ mask,
     int32_t* __restrict__ pos_ids, int32_t* __restrict__ type_ids, float* __restrict__ inv_norm,
     float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   const int S = 1 + M * (T + 1);
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
     float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ dproj,
     float* __restrict__ dpos_emb, float* __restrict__ dtype_emb, float* __restrict__ dgamma,
     float* __restrict__ dbeta) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
@@ -182,6 +186,8 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_fwd_kernel(
     float* __restrict__ t, const float* __restrict__ res, const float* __restrict__ gamma,
     const float* __restrict__ beta, int64_t rows, float eps, float p_drop, uint64_t seed,
     uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ y, float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
@@ -221,6 +227,8 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
     const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr,
     float* __restrict__ dz, float* __restrict__ dt, float* __restrict__ dgamma,
     float* __restrict__ dbeta, float* __restrict__ dbias) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
@@ -283,6 +291,8 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
     const float* __restrict__ scores, const float* __restrict__ mask, int B, int H, int S, int ld,
     float scale, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ Psoft,
     float* __restrict__ Pdrop) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)B * H * S;
@@ -339,6 +349,8 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_fwd_kernel(
 __global__ void __launch_bounds__(WARPS * 32) softmax_bwd_kernel(
     float* __restrict__ dP, const float* __restrict__ Psoft, int64_t rows, int S, int ld,
     float scale, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const int lane = threadIdx.x & 31;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
@@ -386,6 +398,8 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS * 32) readout_fwd_kernel(
     const float* __restrict__ h, int B, int S, int M, int T, float* __restrict__ v,
     float* __restrict__ inv_norm) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -404,6 +418,8 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS * 32) readout_bwd_kernel(
     const float* __restrict__ dv, const float* __restrict__ v, const float* __restrict__ inv_norm,
     int B, int S, int M, int T, float* __restrict__ dh) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int d = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -433,6 +449,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t rows, int n,
                                                      int64_t ld, int rb, int64_t rbs,
                                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int c4 = blockIdx.x * 32 + threadIdx.x;        // float4 column index
   const int ty = threadIdx.y;
@@ -471,6 +489,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ in,
                                                       float* __restrict__ out, int64_t rows, int n4,
                                                       float p, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr) {
+  pdl_trigger();
+  pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const float inv_keep = 1.f / (1.f - p);
   const int64_t total = rows * n4;
@@ -503,7 +523,7 @@ int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const
   MMT_ARG_CHECK(B > 0 && M > 0 && T > 0 && max_pos > 0, MMT_E_SHAPE, "mmt_embed_ln_fwd: bad shape B=%d M=%d T=%d", B, M, T);
   CHECK_D(d); CHECK_P(p_drop);
   const int64_t rows = (int64_t)B * (1 + M * (T + 1));
-  DISPATCH_VEC(d, (embed_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(embed_ln_fwd_kernel<V>, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       proj, ft, ind, type_idx, pos_emb, type_emb, gamma, beta, B, M, T, max_pos, eps, p_drop, seed,
       site, g_step_ctr, h, mask, pos_ids, type_ids, inv_norm, mean, rstd)));
   MMT_LAUNCH_CHECK("embed_ln_fwd");
@@ -522,7 +542,7 @@ int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
   const int64_t rows = (int64_t)B * (1 + M * (T + 1));
   int grid = row_grid(rows);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
-  DISPATCH_VEC(d, (embed_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(embed_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, M, T, p_drop,
       seed, site, g_step_ctr, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
   MMT_LAUNCH_CHECK("embed_ln_bwd");
@@ -535,7 +555,7 @@ int mmt_res_ln_fwd(float* t, const float* r, const float* gamma, const float* be
   MMT_ARG_CHECK(t && r && gamma && beta && y && mean && rstd, MMT_E_ARG, "mmt_res_ln_fwd: null pointer");
   CHECK_D(d); CHECK_P(p_drop);
   if (rows == 0) return 0;
-  DISPATCH_VEC(d, (res_ln_fwd_kernel<V><<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(res_ln_fwd_kernel<V>, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       t, r, gamma, beta, rows, eps, p_drop, seed, site, g_step_ctr, y, mean, rstd)));
   MMT_LAUNCH_CHECK("res_ln_fwd");
   return 0;
@@ -551,7 +571,7 @@ int mmt_res_ln_bwd(const float* dy, const float* dy2, const float* z, const floa
   if (rows == 0) return 0;
   int grid = row_grid(rows);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
-  DISPATCH_VEC(d, (res_ln_bwd_kernel<V><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(
+  DISPATCH_VEC(d, (launch_pdl(res_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, g_step_ctr, dz, dt, dgamma, dbeta, dbias)));
   MMT_LAUNCH_CHECK("res_ln_bwd");
   return 0;
@@ -565,7 +585,7 @@ int mmt_softmax_mask_fwd(const float* scores, const float* mask, int32_t B, int3
   MMT_ARG_CHECK(S > 0 && S <= 128 * SM_MAXC && ld >= S && ld % 4 == 0 && ld <= 128 * SM_MAXC, MMT_E_SHAPE,
                 "mmt_softmax_mask_fwd: S=%d ld=%d unsupported (S <= %d, ld %% 4 == 0)", S, ld, 128 * SM_MAXC);
   CHECK_P(p_drop);
-  softmax_fwd_kernel<<<row_grid((int64_t)B * H * S), WARPS * 32, 0, (cudaStream_t)stream>>>(
+  launch_pdl(softmax_fwd_kernel, dim3(row_grid((int64_t)B * H * S)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       scores, mask, B, H, S, ld, scale, p_drop, seed, site, g_step_ctr, Psoft, Pdrop);
   MMT_LAUNCH_CHECK("softmax_fwd");
   return 0;
@@ -577,7 +597,7 @@ int mmt_softmax_mask_bwd(float* dP, const float* Psoft, int32_t B, int32_t H, in
   MMT_ARG_CHECK(S > 0 && ld >= S && ld % 4 == 0 && ld <= 128 * SM_MAXC, MMT_E_SHAPE, "mmt_softmax_mask_bwd: S=%d ld=%d unsupported", S, ld);
   CHECK_P(p_drop);
   const int64_t rows = (int64_t)B * H * S;
-  softmax_bwd_kernel<<<row_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(dP, Psoft, rows, S, ld, scale, p_drop, seed, site, g_step_ctr);
+  launch_pdl(softmax_bwd_kernel, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream, dP, Psoft, rows, S, ld, scale, p_drop, seed, site, g_step_ctr);
   MMT_LAUNCH_CHECK("softmax_bwd");
   return 0;
 }
@@ -587,7 +607,7 @@ int mmt_readout_norm_fwd(const float* h, int32_t B, int32_t S, int32_t M, int32_
   MMT_ARG_CHECK(h && v && inv_norm, MMT_E_ARG, "mmt_readout_norm_fwd: null pointer");
   MMT_ARG_CHECK(S == 1 + M * (T + 1), MMT_E_SHAPE, "mmt_readout_norm_fwd: S=%d != 1+M*(T+1)", S);
   CHECK_D(d);
-  DISPATCH_VEC(d, (readout_fwd_kernel<V><<<(B * M + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(h, B, S, M, T, v, inv_norm)));
+  DISPATCH_VEC(d, (launch_pdl(readout_fwd_kernel<V>, dim3((B * M + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, (cudaStream_t)stream, h, B, S, M, T, v, inv_norm)));
   MMT_LAUNCH_CHECK("readout_fwd");
   return 0;
 }
@@ -599,7 +619,7 @@ int mmt_readout_norm_bwd(const float* dv, const float* v, const float* inv_norm,
   CHECK_D(d);
   cudaError_t e = cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)B * S * d, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_status(e, "readout_bwd memset");
-  DISPATCH_VEC(d, (readout_bwd_kernel<V><<<(B * M + WARPS - 1) / WARPS, WARPS * 32, 0, (cudaStream_t)stream>>>(dv, v, inv_norm, B, S, M, T, dh)));
+  DISPATCH_VEC(d, (launch_pdl(readout_bwd_kernel<V>, dim3((B * M + WARPS - 1) / WARPS), dim3(WARPS * 32), 0, (cudaStream_t)stream, dv, v, inv_norm, B, S, M, T, dh)));
   MMT_LAUNCH_CHECK("readout_bwd");
   return 0;
 }
@@ -619,8 +639,8 @@ int mmt_colsum(const float* X, int64_t rows, int32_t n, int64_t ld, int32_t rb, 
   int64_t want = (rows + 63) / 64;
   int64_t cap = 4 * num_sms() / gx + 1;
   int gy = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  if (vec) colsum_kernel<true><<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, rows, n, ld, rb, rbs, out);
-  else colsum_kernel<false><<<dim3(gx, gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, rows, n, ld, rb, rbs, out);
+  if (vec) launch_pdl(colsum_kernel<true>, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, X, rows, n, ld, rb, rbs, out);
+  else launch_pdl(colsum_kernel<false>, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, X, rows, n, ld, rb, rbs, out);
   MMT_LAUNCH_CHECK("colsum");
   return 0;
 }
@@ -634,7 +654,7 @@ int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, u
   if (total == 0) return 0;
   int64_t blocks = (total + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  dropout_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n / 4, p, seed, site, g_step_ctr);
+  launch_pdl(dropout_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, in, out, rows, n / 4, p, seed, site, g_step_ctr);
   MMT_LAUNCH_CHECK("dropout");
   return 0;
 }
