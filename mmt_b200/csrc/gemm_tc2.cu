@@ -11,6 +11,8 @@
 // Tiles are ordered m-fastest so the CTAs that run together share the same B (weight) tile in L2.
 // Weight-gradient shapes (few tiles, K = B*S) are split along K into (tile, k-range) work items
 // whose epilogue reduces with red.global.add.v4.f32 into a zeroed C.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace mmt {
@@ -21,10 +23,11 @@ constexpr int BM = 128, BK = 32, UMMA_K = 8;
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr int STG_PITCH = 36;                         // floats; 16 B aligned rows, conflict-free v4 phases
-constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
+constexpr uint32_t STG_BYTES_PER_WARP = 5120;         // 32 x 36 floats (4608 B), rounded up so every warp's tile is 1024 B aligned
 
 struct Tc2Args {
   mmt_gemm_desc d;
+  int c_tma;                                            // plain epilogue: C tiles leave through TMA stores
   int num_m_tiles, num_n_tiles;
   int split_k, kb_per_split, num_kb;
 };
@@ -33,6 +36,7 @@ struct Tc2Args {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_c,
                                                                   const Tc2Args args) {
   constexpr int STAGES = BN == 256 ? 4 : 6;
   constexpr uint32_t B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                               // TMEM lane quarter == output rows 32q..32q+31
-    float* stg = staging + q * (32 * STG_PITCH);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staging) + q * STG_BYTES_PER_WARP);
     const bool vec_ok = ((d.c_ms & 3) == 0) && (((d.c_bs0 | d.c_bs1 | d.bias_bs) & 3) == 0) &&
                         ((((uintptr_t)d.C | (uintptr_t)d.bias | (uintptr_t)d.add | (uintptr_t)d.aux) & 15) == 0);
     const int sub_r = lane >> 3;                          // store phase: row within a group of 4
@@ -166,6 +170,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
         if (nb >= d.N) break;                             // warp-uniform
         float v[32];
         tmem_ld32(acc + (uint32_t)(c * 32), v);
+        if (args.c_tma) {
+          // Plain epilogue (C = alpha * acc [+ bias], optional column sums): the lane's row goes to the
+          // warp's [32 x 32] staging tile in the 128-byte swizzle the tensor map expects and ONE TMA
+          // store writes the tile (rows >= M and columns >= N are clipped by the map).  No transposed
+          // read-back, no per-row address arithmetic: the batched attention products (K = 128 / 218)
+          // were bound by exactly that epilogue work on four warps.
+          const uint32_t stg_u = smem_u32(stg);
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], d.alpha, (nb + j < d.N) ? __ldg(bias + nb + j) : 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= d.alpha;
+          }
+          if (lane == 0) bulk_wait_read0();                   // the previous store has read the tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(stg) + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&map_c, stg_u, nb, m0 + q * 32, z % d.batch_inner, z / d.batch_inner);
+            bulk_commit();
+          }
+          if (d.colsum != nullptr && nb + lane < d.N) {        // lane = column: sum this warp's valid rows
+            const int rows_ok = min(32, d.M - (m0 + q * 32));
+            float cs = 0.f;
+            for (int r = 0; r < rows_ok; ++r)
+              cs += *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(stg) + r * 128 +
+                                                    (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            atomicAdd(d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + nb + lane, cs);
+          }
+          continue;
+        }
         // phase 1: this lane's row -> warp-private staging (row pitch 36 floats)
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -263,6 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);         // this warp no longer reads the accumulator
     }
+    if (args.c_tma && lane == 0) bulk_wait0();             // outstanding C stores complete before the CTA retires
   }
   __syncthreads();
   if (warp == 1) {
@@ -272,7 +313,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, cudaStream_t stream) {
+int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const Tc2Args& args,
+            cudaStream_t stream) {
   constexpr int STAGES = BN == 256 ? 4 : 6;
   constexpr size_t smem = STAGES * (A_BYTES + BN * BK * 4) + 4 * STG_BYTES_PER_WARP + 1024 + 256;
   static bool configured = false;
@@ -284,7 +326,7 @@ int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Tc2Args& args, c
   }
   const int work = args.num_m_tiles * args.num_n_tiles * args.split_k * args.d.batch;
   const int grid = work < num_sms() ? work : num_sms();
-  launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, ma, mb, args);
+  launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, ma, mb, mc, args);
   MMT_LAUNCH_CHECK("gemm_tc2_kernel");
   return 0;
 }
@@ -304,10 +346,19 @@ int dispatch2(const mmt_gemm_desc& d, Tc2Args& args, bool a_mn, bool b_mn, cudaS
   rc = make_tf32_map(&mb, d.B, d.N, d.K, d.b_ns, d.b_ks, b_mn, BN, bo, d.batch_inner, d.b_bs0, d.b_bs1, "B");
   if (rc) return rc;
   args.num_n_tiles = (d.N + BN - 1) / BN;
-  if (!a_mn && !b_mn) return launch2<BN, false, false>(ma, mb, args, stream);
-  if (!a_mn && b_mn) return launch2<BN, false, true>(ma, mb, args, stream);
-  if (a_mn && !b_mn) return launch2<BN, true, false>(ma, mb, args, stream);
-  return launch2<BN, true, true>(ma, mb, args, stream);
+  // plain epilogues leave through TMA stores (32 x 32 tiles, 128-byte swizzle, clipped at M / N)
+  CUtensorMap mc = ma;
+  static const bool tma_epi = [] { const char* e = getenv("MMT_TMA_EPILOGUE"); return !(e && e[0] == '0'); }();
+  args.c_tma = tma_epi && d.epilogue == MMT_EPI_NONE && d.add == nullptr && args.split_k == 1 && d.c_mb == 0 &&
+               (d.c_ms & 3) == 0 && ((d.c_bs0 | d.c_bs1) & 3) == 0 && ((uintptr_t)d.C & 15) == 0;
+  if (args.c_tma) {
+    rc = make_tf32_map(&mc, d.C, d.M, d.N, d.c_ms, 1, false, 32, bo, d.batch_inner, d.c_bs0, d.c_bs1, "C");
+    if (rc) return rc;
+  }
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ma, mb, mc, args, stream);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ma, mb, mc, args, stream);
+  if (a_mn && !b_mn) return launch2<BN, true, false>(ma, mb, mc, args, stream);
+  return launch2<BN, true, true>(ma, mb, mc, args, stream);
 }
 }  // namespace
 

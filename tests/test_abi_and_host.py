@@ -230,3 +230,45 @@ def test_product_path_fails_loudly_without_cuda():
   with pytest.raises(RuntimeError, match="CUDA"):
     net(batch["token_ids"], batch["features"], batch["features_t"], batch["features_ind"],
         batch["features_avgpool"], batch["features_maxpool"], batch["query_masks"])
+
+
+def test_grad_reducer_covers_the_buffer_exactly_once():
+  """GradReducer (data-parallel gradient exchange in pieces): early pieces + finish() must cover the flat
+  buffer exactly once, and overlapping pieces are a bug that is reported, not summed twice."""
+  import torch
+  from mmt_b200 import parallel
+
+  class _Work:
+    def wait(self):
+      pass
+
+  calls = []
+
+  class _Dist:
+    class ReduceOp:
+      SUM = "sum"
+
+    @staticmethod
+    def all_reduce(t, op=None, group=None, async_op=False):
+      calls.append((t.storage_offset(), t.numel()))
+      t.mul_(2.0)                                   # stand-in for SUM over two identical ranks
+      return _Work()
+
+  real = parallel.dist
+  parallel.dist = _Dist
+  try:
+    g = torch.arange(100, dtype=torch.float32)
+    red = parallel.GradReducer(g, None)
+    red.reduce(60, 20)
+    red.reduce(10, 30)
+    red.reduce(0, 0)                                # empty pieces are ignored
+    red.finish()
+    assert sorted(calls) == [(0, 10), (10, 30), (40, 20), (60, 20), (80, 20)]
+    assert torch.equal(g, 2 * torch.arange(100, dtype=torch.float32))
+    red = parallel.GradReducer(g, None)
+    red.reduce(0, 50)
+    red.reduce(40, 20)
+    with pytest.raises(RuntimeError):
+      red.finish()
+  finally:
+    parallel.dist = real
