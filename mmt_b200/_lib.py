@@ -103,7 +103,9 @@ def check(rc, what):
 
 
 def stream_ptr():
-  return torch.cuda.current_stream().cuda_stream
+  """Raw cudaStream_t of torch's current stream on the current device (the C-level accessor: the python
+  Stream object costs ~13 us to build, and a train step asks ~100 times)."""
+  return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def ptr(t, offset=0):

@@ -238,7 +238,14 @@ class CENet(nn.Module):
     return mod._parameters[leaf]
 
   def _hot_params(self):
-    return [self._param(n) for n in self._names]
+    """The Parameters that live in the flat buffer, in layout order.  The list is cached (the objects
+    survive .to(): _sync_device only re-points their .data) and re-validated by identity."""
+    cache = self.__dict__.get("_hot_cache")
+    if cache is None or len(cache) != len(self._names) or cache[0] is not self._param(self._names[0]):
+      cache = [self._param(n) for n in self._names]
+      self.__dict__["_hot_cache"] = cache
+      self.__dict__["_grad_views"] = None
+    return cache
 
   def _apply(self, fn, *a, **kw):
     out = super()._apply(fn, *a, **kw)
@@ -294,13 +301,16 @@ class CENet(nn.Module):
   def _publish_grads(self, gflat, accumulate):
     """Expose the flat gradient as per-parameter .grad views (reference names).  The pooler's
     parameters get no gradient, as in the reference (its output is discarded, model.py:583-584)."""
-    for n in self._names:
-      if n.startswith("vid_bert.pooler."):
+    params = self._hot_params()
+    views = self.__dict__.get("_grad_views")
+    if views is None or views[0] != gflat.data_ptr():        # per-parameter views of this gradient buffer
+      views = (gflat.data_ptr(), [None if n.startswith("vid_bert.pooler.") else self.layout.view(gflat, n)
+                                  for n in self._names])
+      if gflat is self._gflat:
+        self.__dict__["_grad_views"] = views
+    for p, v in zip(params, views[1]):
+      if v is None or not p.requires_grad:
         continue
-      p = self._param(n)
-      if not p.requires_grad:
-        continue
-      v = self.layout.view(gflat, n)
       if accumulate and p.grad is not None:
         p.grad.add_(v)
       else:

@@ -58,11 +58,13 @@ class FusedAdam:
     g = net._grad_flat()
     # gradients are normally views of net._gflat (EncodeFn publishes them without copies); if the
     # caller accumulated / replaced them, gather them back into the flat layout first
-    for name in net._names:
-      p = net._param(name)
+    views = net.__dict__.get("_grad_views")
+    for i, p in enumerate(net._hot_params()):
       if p.grad is None:
         continue
-      v = net.layout.view(g, name)
+      if views is not None and views[0] == g.data_ptr() and p.grad is views[1][i]:
+        continue                                            # the common case: already a view of g
+      v = net.layout.view(g, net._names[i])
       if p.grad.data_ptr() != v.data_ptr():
         v.copy_(p.grad)
     self.t += 1
