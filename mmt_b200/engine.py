@@ -510,7 +510,9 @@ def sims_forward(vid, txt, vw, tw, caps, merge_avg):
   return sims, dots
 
 
-def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg):
+def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg, precision=PREC_FP32):
+  """Backward of sims_forward.  `precision` applies to the two gradient products only (the forward dot
+  products always stay fp32 FMAs: ranking at the similarity boundary must be exact)."""
   lib = _lib.load()
   Nv, M, d = vid.shape
   Nq = txt.shape[0]
@@ -522,10 +524,12 @@ def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg):
   # dtxt[:, m, :] = ddots_m @ vid_m ; dvid[:, m, :] = ddots_m^T @ txt_m
   dtxt = torch.empty_like(txt)
   dvid = torch.empty_like(vid)
+  tc = precision == PREC_TF32 and Nv % 4 == 0 and Nq % 4 == 0          # TMA strides: 16-byte multiples
+  prec = PREC_TF32 if tc else PREC_FP32
   gemm(Nq, d, Nv, ddots, Nv, 1, vid, 1, M * d, dtxt, M * d, batch=M, a_bs=(Nq * Nv, 0), b_bs=(d, 0),
-       c_bs=(d, 0))
+       c_bs=(d, 0), precision=prec)
   gemm(Nv, d, Nq, ddots, 1, Nv, txt, 1, M * d, dvid, M * d, batch=M, a_bs=(Nq * Nv, 0), b_bs=(d, 0),
-       c_bs=(d, 0))
+       c_bs=(d, 0), precision=prec)
   return dvid, dtxt, dtw
 
 

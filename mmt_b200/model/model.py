@@ -70,19 +70,19 @@ class EncodeFn(torch.autograd.Function):
 class SimsFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, vid, txt, vw, tw, caps, merge_avg):
+  def forward(ctx, vid, txt, vw, tw, caps, merge_avg, bwd_precision=engine.PREC_FP32):
     vid, txt, vw, tw = vid.contiguous(), txt.contiguous(), vw.contiguous(), tw.contiguous()
     sims, dots = engine.sims_forward(vid, txt, vw, tw, caps, merge_avg)
     ctx.save_for_backward(vid, txt, vw, tw, dots)
-    ctx.caps, ctx.merge_avg = caps, merge_avg
+    ctx.caps, ctx.merge_avg, ctx.bwd_precision = caps, merge_avg, bwd_precision
     return sims
 
   @staticmethod
   def backward(ctx, dsims):
     vid, txt, vw, tw, dots = ctx.saved_tensors
     dvid, dtxt, dtw = engine.sims_backward(dsims.contiguous(), dots, vid, txt, vw, tw, ctx.caps,
-                                           ctx.merge_avg)
-    return dvid, dtxt, None, dtw, None, None
+                                           ctx.merge_avg, ctx.bwd_precision)
+    return dvid, dtxt, None, dtw, None, None, None
 
 
 def sharded_cross_view_inner_product(vid_embds, text_embds, vid_weights, text_weights, subspaces,
@@ -375,7 +375,7 @@ class CENet(nn.Module):
     merge = "avg" if self.training else self.test_caption_mode
     self.merge_caption_similarities = merge
     if out == "conf":
-      conf = SimsFn.apply(vid, txt, vid_weights, tw, caps, merge == "avg")
+      conf = SimsFn.apply(vid, txt, vid_weights, tw, caps, merge == "avg", self.cfg.precision)
       return {"modalities": mods, "cross_view_conf_matrix": conf}
     return {
         "vid_embds": vid,                                             # [b, M, d]
