@@ -354,38 +354,56 @@ __global__ void __launch_bounds__(WARPS * 32) softmax_bwd_kernel(
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
   const int lane = threadIdx.x & 31;
   const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  // each lane owns 8 consecutive columns per chunk: one Philox call = exactly its 8 dropout decisions
+  constexpr int NCH = SM_MAXC / 2;
   for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows;
        r += (int64_t)gridDim.x * WARPS) {
-    float4 da[SM_MAXC], a[SM_MAXC];
+    float da[NCH][8], a[NCH][8];
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < SM_MAXC; ++c) {
-      const int j = 4 * (lane + 32 * c);
-      if (j < ld) {
-        da[c] = *reinterpret_cast<const float4*>(dP + r * ld + j);
-        a[c] = *reinterpret_cast<const float4*>(Psoft + r * ld + j);
-        if (p_drop > 0.f) {
-          float4 sc = dropout_scale4_h16(seed, site, (uint32_t)r, lane + 32 * c, p_drop, inv_keep);
-          F4_OP(da[c], da[c].x * sc.x, da[c].y * sc.y, da[c].z * sc.z, da[c].w * sc.w);
-        }
-        float* pa = reinterpret_cast<float*>(&a[c]);
-        float* pd = reinterpret_cast<float*>(&da[c]);
+    for (int c = 0; c < NCH; ++c) {
+      const int j = 8 * (lane + 32 * c);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (j + q >= S) { pa[q] = 0.f; pd[q] = 0.f; }
-          dot += pa[q] * pd[q];
+      for (int q = 0; q < 8; ++q) { da[c][q] = 0.f; a[c][q] = 0.f; }
+      if (j < ld) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (j + 4 * h < ld) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dP + r * ld + j + 4 * h);
+            const float4 a4 = *reinterpret_cast<const float4*>(Psoft + r * ld + j + 4 * h);
+            da[c][4 * h] = d4.x; da[c][4 * h + 1] = d4.y; da[c][4 * h + 2] = d4.z; da[c][4 * h + 3] = d4.w;
+            a[c][4 * h] = a4.x; a[c][4 * h + 1] = a4.y; a[c][4 * h + 2] = a4.z; a[c][4 * h + 3] = a4.w;
+          }
+        }
+        if (p_drop > 0.f) {
+          float sc[8];
+          dropout_scale8_h16(seed, site, (uint32_t)r, (uint32_t)(j >> 3), p_drop, inv_keep, sc);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) da[c][q] *= sc[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (j + q >= S) { a[c][q] = 0.f; da[c][q] = 0.f; }
+          dot = fmaf(a[c][q], da[c][q], dot);
         }
       }
     }
     dot = warp_sum(dot);
 #pragma unroll
-    for (int c = 0; c < SM_MAXC; ++c) {
-      const int j = 4 * (lane + 32 * c);
+    for (int c = 0; c < NCH; ++c) {
+      const int j = 8 * (lane + 32 * c);
       if (j < ld) {
-        float4 o;
-        F4_OP(o, a[c].x * (da[c].x - dot) * scale, a[c].y * (da[c].y - dot) * scale,
-              a[c].z * (da[c].z - dot) * scale, a[c].w * (da[c].w - dot) * scale);
-        *reinterpret_cast<float4*>(dP + r * ld + j) = o;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (j + 4 * h < ld) {
+            float4 o;
+            o.x = a[c][4 * h] * (da[c][4 * h] - dot) * scale;
+            o.y = a[c][4 * h + 1] * (da[c][4 * h + 1] - dot) * scale;
+            o.z = a[c][4 * h + 2] * (da[c][4 * h + 2] - dot) * scale;
+            o.w = a[c][4 * h + 3] * (da[c][4 * h + 3] - dot) * scale;
+            *reinterpret_cast<float4*>(dP + r * ld + j + 4 * h) = o;
+          }
+        }
       }
     }
   }
