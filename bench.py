@@ -411,8 +411,9 @@ def roofline_ffn(net, w, B, dev, args):
   peak = bf16 / 2.0 if args.precision == "tf32" else bf16
   ach = flops / (ms / 1e3) / 1e12
   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at C2 from the committed ncu capture
-  # (profiles/r01_gemm_pair_and_attention_ncu_raw.csv: 86.9 MB + 284.8 MB); algorithmic 377.7 MB
-  traffic = 371.7e6 if (args.precision == "tf32" and BS == 13952) else None
+  # (profiles/r01_gemm_pair_and_attention_ncu_raw.csv: 37.4 MB read + 282.6 MB written at kernel end; an
+  # earlier capture of the round had 86.9 + 284.8 MB); algorithmic 377.7 MB -- no re-reads either way
+  traffic = 320.0e6 if (args.precision == "tf32" and BS == 13952) else None
   return {"kernel": "FFN-up GEMM+bias+erf-GELU %dx%dx%d (%s)" % (BS, ff, d, args.precision),
           "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
           "traffic": traffic, "ms_per_launch": ms,
