@@ -270,6 +270,42 @@ def run_b200(args):
   if graphed is not None:
     graphed.close()
 
+  if args.trace and rank != 0:
+    for i in range(3):                      # every rank takes part in the traced steps' collectives
+      value_step(i)
+    torch.cuda.synchronize()
+  if args.trace and rank == 0:
+    # development aid: kernel timeline of 3 steps on rank 0 (torch.profiler / CUPTI): busy vs idle time of
+    # the device and the share of NCCL kernels, printed to stderr (never part of a reported number)
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+      for i in range(3):
+        value_step(i)
+      torch.cuda.synchronize()
+    ev = [(e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type.name == "CUDA"]
+    ev.sort()
+    t0, t1 = ev[0][0], max(e[1] for e in ev)
+    busy, cur_s, cur_e = 0.0, ev[0][0], ev[0][1]
+    for s_, e_, _ in ev[1:]:
+      if s_ > cur_e:
+        busy += cur_e - cur_s
+        cur_s, cur_e = s_, e_
+      else:
+        cur_e = max(cur_e, e_)
+    busy += cur_e - cur_s
+    nccl = sum(e_ - s_ for s_, e_, n in ev if "nccl" in n.lower())
+    import collections
+    agg = collections.defaultdict(float)
+    for s_, e_, n in ev:
+      agg[n[:70]] += e_ - s_
+    sys.stderr.write("[trace] 3 steps: span %.2f ms, device busy %.2f ms, idle %.2f ms, nccl kernels %.2f ms\n" %
+                     ((t1 - t0) / 1e3, busy / 1e3, (t1 - t0 - busy) / 1e3, nccl / 1e3))
+    for n, v in sorted(agg.items(), key=lambda kv: -kv[1])[:14]:
+      sys.stderr.write("[trace]   %8.1f us  %s\n" % (v, n))
+  if args.trace and world > 1:
+    dist.barrier()
+
   # ---- end to end through the public API with HOST buffers ("e2e") ----
   # Every timed step performs one pinned-host -> device copy of a full input batch and one
   # device -> host read of the loss.  The copy of step i+1's batch runs on a side stream while
@@ -578,6 +614,7 @@ def main():
                   help="replay the step as one CUDA graph for `value` (mmt_b200/graph.py); measured gain on "
                        "B200 is < 1 % because the step is GPU-bound, so eager launches are the default")
   ap.add_argument("--no-hbm-probe", action="store_true")
+  ap.add_argument("--trace", action="store_true", help="print a kernel-timeline summary of 3 steps (rank 0)")
   ap.add_argument("--no-graph-e2e", action="store_true",
                   help="e2e through eager CENet.forward only (skip the GraphedTrainStep arm)")
   args = ap.parse_args()

@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(128) sdot_block_kernel(const mmt_gemm_desc d, 
 }  // namespace
 
 int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream) {
-  if (d.M <= 96 && d.N <= 96 && d.a_ks == 1 && d.b_ks == 1 && d.a_kb == 0 && d.K >= 128 && (d.K & 3) == 0 &&
+  // up to 256 x 256 outputs (the data-parallel head at global batch 128 / 256): the 128-tile kernel
+  // would run 7-28 CTAs there
+  if (d.M <= 256 && d.N <= 256 && d.a_ks == 1 && d.b_ks == 1 && d.a_kb == 0 && d.K >= 128 && (d.K & 3) == 0 &&
       ((d.a_ms | d.b_ns | d.a_bs0 | d.a_bs1 | d.b_bs0 | d.b_bs1) & 3) == 0 &&
       ((((uintptr_t)d.A | (uintptr_t)d.B)) & 15) == 0 && d.epilogue == MMT_EPI_NONE && d.add == nullptr) {
     const int bm = (d.M + DB - 1) / DB, bn = (d.N + DB - 1) / DB;   // one warp per 8 x 8 outputs

@@ -58,6 +58,11 @@ class GradReducer:
                                       async_op=True))
     self.done.append((off, n))
 
+  def skip(self, off, n):
+    """Exclude a piece from the exchange altogether (parameters that never receive a gradient)."""
+    if n > 0:
+      self.done.append((off, n))
+
   def finish(self):
     pos = 0
     for off, n in sorted(self.done) + [(self.gflat.numel(), 0)]:
@@ -98,9 +103,13 @@ class DPEncodeFn(torch.autograd.Function):
     dtext_g = engine.head_backward(net.cfg, net.flat, gflat, sv_h, dtxt.contiguous(),
                                    dtw.contiguous(), need_dtext=ctx.needs_input_grad[1])
     red = GradReducer(gflat, group)
+    small_end = getattr(net.layout, "small_numel", 0)
     for off, n in head_segments(net.layout):
       gflat[off:off + n].mul_(1.0 / w)
-      red.reduce(off, n)
+      if off >= small_end:            # the head's weight matrices go out now; its few small vectors stay
+        red.reduce(off, n)            # with the rest of the small region (one piece at the end)
+    for off, n in getattr(net.layout, "no_grad_ranges", lambda: [])():
+      red.skip(off, n)                # e.g. the unused pooler: nothing to exchange
     layer_range = getattr(net.layout, "layer_big_range", None)
     engine.video_backward(net.cfg, net.flat, gflat, sv_v, dvid[rank * bl:(rank + 1) * bl].contiguous(),
                           on_layer_done=(lambda l: red.reduce(*layer_range(l))) if layer_range else None)

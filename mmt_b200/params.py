@@ -114,6 +114,11 @@ class Layout:
   def off(self, name):
     return self.segments[name].offset
 
+  def no_grad_ranges(self):
+    """Weight matrices that never receive a gradient (the pooler, reference model.py:583-584)."""
+    seg = self.segments["vid_bert.pooler.dense.weight"]
+    return [(seg.offset, _align(seg.numel))]
+
   def layer_big_range(self, l):
     """(offset, numel) of encoder layer l's weight matrices (Wq|Wk|Wv, Wo, W1, W2: one contiguous block)."""
     p = "vid_bert.encoder.layer.%d." % l

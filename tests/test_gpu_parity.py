@@ -106,6 +106,24 @@ def test_gemm_epilogues_batch_remap_splitk(dev):
   assert H.rel_err(dW, dY.double().t() @ X.double()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,batch", [(64, 64, 512, 7), (130, 200, 256, 3), (256, 256, 128, 2), (8, 9, 132, 1)])
+def test_gemm_fp32_warp_block_dot_path(dev, M, N, K, batch):
+  """Small outputs with both operands contiguous along k (the similarity dot products, also at the
+  data-parallel global batch): one warp per 8 x 8 block, strided batches, ragged edges, bias."""
+  from mmt_b200 import _lib
+  g = torch.Generator().manual_seed(M + N)
+  ld = K + 4
+  A = torch.randn(M, batch, ld, generator=g).to(dev)           # rows strided by batch * ld, batch stride ld
+  B = torch.randn(N, batch, ld, generator=g).to(dev)
+  bias = torch.randn(batch, N, generator=g).to(dev)
+  C = torch.full((batch, M, N), float("nan"), device=dev)
+  _lib.gemm(M, N, K, A, batch * ld, 1, B, batch * ld, 1, C, N, batch=batch, a_bs=(ld, 0), b_bs=(ld, 0),
+            c_bs=(M * N, 0), bias=bias, bias_bs=N, alpha=0.5)
+  ref = 0.5 * torch.einsum("mbk,nbk->bmn", A[..., :K].double(), B[..., :K].double()) + bias.double()[:, None, :]
+  assert torch.isfinite(C).all()
+  assert H.rel_err(C, ref) < 2e-6
+
+
 def test_gemm_rejects_bad_arguments(dev):
   from mmt_b200 import _lib
   A = torch.zeros(4, 4, device=dev)
