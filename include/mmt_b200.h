@@ -240,6 +240,17 @@ int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Retrieval ranks on the device (model/metric.py:26-150 t2v_metrics, :152-230 v2t_metrics): 0-based
+ * rank of the ground truth with ties averaged, by exact counting on the fp32 similarities (no sort).
+ * sims [Nq, Nv] (rows = captions, video-major, Nq = Nv * caps).  v2t = 0: ranks[Nq], rank of video
+ * i / caps in row i.  v2t = 1: ranks[Nv], for video v the best rank of its own captions among ALL
+ * captions of column v; valid[Nq] (may be NULL) marks existing captions -- missing ones are neither
+ * ranked nor candidates (the reference moves them to distance 1e8); +inf if a video has none.
+ * ------------------------------------------------------------------------------------------- */
+int mmt_retrieval_ranks(const float* sims, const int32_t* valid, int32_t Nq, int32_t Nv, int32_t v2t,
+                        float* ranks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mmt_softmax_mask_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p]),
     "mmt_attention_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p, c_p, c_p, c_p,
                                   c_i32, c_p]),
+    "mmt_retrieval_ranks": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
     "mmt_readout_norm_fwd": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     "mmt_readout_norm_bwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),
     "mmt_geu_gate_fwd": (c_i32, [c_p] * 6 + [c_i32] * 4 + [c_f, c_f] + [c_p] * 6 + [c_p]),

@@ -547,6 +547,66 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Retrieval ranks (model/metric.py:26-230): position of the ground truth in the row sorted by
+// DESCENDING similarity, ties averaged = #(strictly better) + (#equal - 1) / 2.  Pure counting on
+// the fp32 values (the reference compares the negated floats): exact, no sort.
+// ------------------------------------------------------------------------------------------
+// t2v: one warp per query (caption) i; ground-truth video = i / caps.
+__global__ void __launch_bounds__(256) ranks_t2v_kernel(const float* __restrict__ sims, int Nq, int Nv, int caps,
+                                                        float* __restrict__ ranks) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= Nq) return;
+  const float* row = sims + (int64_t)i * Nv;
+  const float g = row[i / caps];
+  int better = 0, equal = 0;
+  for (int j = lane; j < Nv; j += 32) {
+    const float x = row[j];
+    better += x > g;
+    equal += x == g;
+  }
+  better = warp_sum_int(better);
+  equal = warp_sum_int(equal);
+  if (lane == 0) ranks[i] = (float)better + 0.5f * (float)(equal - 1);
+}
+
+// v2t: one block per video v; the candidates are ALL captions (column v of sims), captions whose mask is
+// 0 count as infinitely far (metric.py:187-192); result = best rank over v's own unmasked captions
+// (inf when it has none, as np.inf in the reference).
+__global__ void __launch_bounds__(256) ranks_v2t_kernel(const float* __restrict__ sims, const int32_t* __restrict__ valid,
+                                                        int Nq, int Nv, int caps, float* __restrict__ ranks) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int s_better[8], s_equal[8];
+  const int v = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float best = INFINITY;
+  for (int own = v * caps; own < (v + 1) * caps; ++own) {
+    if (valid != nullptr && valid[own] == 0) continue;      // block-uniform
+    const float g = sims[(int64_t)own * Nv + v];
+    int better = 0, equal = 0;
+    for (int c = threadIdx.x; c < Nq; c += blockDim.x) {
+      if (valid != nullptr && valid[c] == 0) continue;      // at distance 1e8: never better, never equal
+      const float x = sims[(int64_t)c * Nv + v];
+      better += x > g;
+      equal += x == g;
+    }
+    better = warp_sum_int(better);
+    equal = warp_sum_int(equal);
+    __syncthreads();
+    if (lane == 0) { s_better[warp] = better; s_equal[warp] = equal; }
+    __syncthreads();
+    int tb = 0, te = 0;
+    for (int w = 0; w < 8; ++w) { tb += s_better[w]; te += s_equal[w]; }
+    best = fminf(best, (float)tb + 0.5f * (float)(te - 1));
+  }
+  if (threadIdx.x == 0) ranks[v] = best;
+}
+
 }  // namespace
 }  // namespace mmt
 
@@ -675,6 +735,20 @@ int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   if (blocks < 1) blocks = 1;
   launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale);
   MMT_LAUNCH_CHECK("adam");
+  return 0;
+}
+
+int mmt_retrieval_ranks(const float* sims, const int32_t* valid, int32_t Nq, int32_t Nv, int32_t v2t,
+                        float* ranks, void* stream) {
+  MMT_ARG_CHECK(sims && ranks, MMT_E_ARG, "mmt_retrieval_ranks: null pointer");
+  MMT_ARG_CHECK(Nv >= 1 && Nq >= Nv && Nq % Nv == 0, MMT_E_SHAPE, "mmt_retrieval_ranks: Nq=%d must be a multiple of Nv=%d", Nq, Nv);
+  const int caps = Nq / Nv;
+  if (v2t) {
+    launch_pdl(ranks_v2t_kernel, dim3(Nv), dim3(256), 0, (cudaStream_t)stream, sims, valid, Nq, Nv, caps, ranks);
+  } else {
+    launch_pdl(ranks_t2v_kernel, dim3((Nq + 7) / 8), dim3(256), 0, (cudaStream_t)stream, sims, Nq, Nv, caps, ranks);
+  }
+  MMT_LAUNCH_CHECK("retrieval_ranks");
   return 0;
 }
 

@@ -788,3 +788,28 @@ def test_single_sample_training_batch_raises_like_batchnorm(dev):
   with torch.no_grad():
     out = net(**H.batch_kwargs(batch, "cuda"))["cross_view_conf_matrix"]     # eval: running stats
   assert tuple(out.shape) == (1, 1) and torch.isfinite(out).all()
+
+
+def test_retrieval_metrics_on_gpu_match_reference_golden_and_oracle(dev, golden_dir):
+  """Eval path: ranks counted on the device reproduce every scalar the reference's
+  t2v_metrics / v2t_metrics produced for the fixture (ties, masked captions) and, at eval scale with
+  heavy ties, the oracle's restatement rank for rank (integer / half-integer values: exact)."""
+  import numpy as np
+  from mmt_b200.model import metric
+  fx = np.load(os.path.join(golden_dir, "metrics.npz"))
+  sims, qm = fx["sims"], fx["query_masks"]
+  t2v, v2t = metric.t2v_metrics(sims, qm), metric.v2t_metrics(torch.from_numpy(sims).to(dev), qm)
+  for k in ("R1", "R5", "R10", "R50", "MedR", "MeanR", "geometric_mean_R1-R5-R10"):
+    np.testing.assert_allclose(t2v[k], fx["t2v/" + k], rtol=1e-9, err_msg="t2v/" + k)
+    np.testing.assert_allclose(v2t[k], fx["v2t/" + k], rtol=1e-9, err_msg="v2t/" + k)
+  rng = np.random.RandomState(11)
+  for nv, caps, decimals in ((1000, 20, 1), (333, 1, 2), (64, 3, 0)):
+    big = np.round(rng.randn(nv * caps, nv), decimals).astype(np.float32)
+    m = (rng.rand(nv, caps) > 0.1).astype(np.int32)
+    m[:, 0] = 1
+    if caps > 1:
+      m[5, :] = 0                                     # a video without any caption: v2t rank = inf
+    r_t2v = metric.retrieval_ranks(big, None, v2t=False)
+    r_v2t = metric.retrieval_ranks(big, m, v2t=True)
+    assert np.array_equal(r_t2v, O.retrieval_ranks(big))
+    assert np.array_equal(r_v2t, O.retrieval_ranks_v2t(big, m))

@@ -137,3 +137,15 @@ def test_retrieval_ranks_golden(golden_dir):
   np.testing.assert_allclose(100.0 * np.mean(ranks < 10), fx["t2v/R10"], rtol=1e-9)
   np.testing.assert_allclose(np.median(ranks) + 1, fx["t2v/MedR"], rtol=1e-9)
   np.testing.assert_allclose(np.mean(ranks) + 1, fx["t2v/MeanR"], rtol=1e-9)
+
+
+def test_retrieval_metrics_v2t_and_all_keys_golden(golden_dir):
+  """Every scalar the reference's t2v_metrics / v2t_metrics returned for the fixture (ties, two masked
+  captions): the oracle's rank restatements + cols2metrics reproduce them."""
+  fx = _load(golden_dir, "metrics.npz")
+  qm = fx["query_masks"]
+  t2v = O.cols2metrics(O.retrieval_ranks(fx["sims"], qm), int(qm.sum()))
+  v2t = O.cols2metrics(O.retrieval_ranks_v2t(fx["sims"], qm), fx["sims"].shape[1])
+  for k in ("R1", "R5", "R10", "R50", "MedR", "MeanR", "geometric_mean_R1-R5-R10"):
+    np.testing.assert_allclose(t2v[k], fx["t2v/" + k], rtol=1e-9, err_msg="t2v/" + k)
+    np.testing.assert_allclose(v2t[k], fx["v2t/" + k], rtol=1e-9, err_msg="v2t/" + k)
