@@ -20,6 +20,9 @@ class GraphedTrainStep:
   """
 
   def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3):
+    if getattr(net, "_dp", False):
+      raise NotImplementedError("GraphedTrainStep: capturing the data-parallel step (NCCL collectives inside "
+                                "the graph) is not supported yet; use the eager step with enable_data_parallel()")
     self.net, self.crit, self.opt = net, crit, opt
     self.kw, self.text = kwargs, text
     dev = net.flat.device
