@@ -1,13 +1,17 @@
-// Persistent tcgen05 TF32 GEMM (large un-batched problems): one CTA per SM walks a static list of
-// 128 x 256 output tiles.
+// Persistent tcgen05 TF32 GEMM on single CTAs: one CTA per SM walks a static list of 128 x 256 (or
+// 128 x 128) output tiles, also across (batch_outer, batch_inner) work items addressed through rank-4
+// tensor maps -- the batched attention products and the problems too small for the CTA-pair kernel.
 //
-//   warp 0    TMA producer     4-stage ring of {A 128x32, B 256x32} fp32 tiles (48 KB / stage)
+//   warp 0    TMA producer     4-stage ring of {A 128x32, B 256x32} fp32 tiles (48 KB / stage);
+//                              6 stages of 32 KB for the 128-wide tile
 //   warp 1    MMA issuer       tcgen05.mma kind::tf32 M=128 N=256 K=8; the 512 TMEM columns hold TWO
 //                              accumulators so tile i+1's main loop overlaps tile i's epilogue
 //   warps 2-5 epilogue         tcgen05.ld -> per-warp shared-memory transpose -> fused
 //                              bias / residual / erf-GELU / GELU' and fully coalesced 128-bit
 //                              global loads/stores (each store instruction covers 4 complete
-//                              128-byte row segments)
+//                              128-byte row segments); plain epilogues (alpha, bias, column sums)
+//                              instead write the lane's row to a 128-byte-swizzled 32 x 32 tile and
+//                              leave through ONE TMA store per tile (see the epilogue)
 // Tiles are ordered m-fastest so the CTAs that run together share the same B (weight) tile in L2.
 // Weight-gradient shapes (few tiles, K = B*S) are split along K into (tile, k-range) work items
 // whose epilogue reduces with red.global.add.v4.f32 into a zeroed C.

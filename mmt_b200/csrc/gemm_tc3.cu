@@ -1,17 +1,20 @@
 // Persistent tcgen05 TF32 GEMM on CTA PAIRS (cta_group::2): two CTAs of a cluster (one per SM of a TPC)
 // own one 256 x 256 output tile.  Each CTA loads its 128 rows of A and only HALF of the B tile
 // (128 of the 256 n-rows); the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=256, K=8), the
-// tensor cores of both SMs read both halves.  Per SM this needs 64 B/cycle of operand traffic
-// instead of the 96 B/cycle of the 1-CTA 128x256 kernel (gemm_tc2.cu), which is what bounds the
-// fp32-operand main loop on B200 (ncu: ~55 % tensor-pipe at ~50 B/cycle/SM ingest).
-// Everything else follows gemm_tc2.cu:
+// tensor cores of both SMs read both halves.  Per SM and k-step this ingests 256 operand rows for a
+// 128 x 256 output slice instead of the 384 rows of the 1-CTA 128x256 kernel (gemm_tc2.cu); operand
+// ingest is what bounds the fp32-operand main loop on B200.
 //
-//   warp 0    TMA producer     4-stage ring of {A 128x32, B 256x32} fp32 tiles (48 KB / stage)
-//   warp 1    MMA issuer       tcgen05.mma kind::tf32 M=128 N=256 K=8; the 512 TMEM columns hold TWO
-//                              accumulators so tile i+1's main loop overlaps tile i's epilogue
-//   warps 2-5 epilogue         tcgen05.ld -> per-warp shared-memory transpose -> fused
-//                              bias / residual / erf-GELU / GELU' and fully coalesced 128-bit
-//                              global loads/stores (each store instruction covers 4 complete
+//   warp 0    TMA producer     5-stage ring of {A 128x32, B 128x32} fp32 tiles per CTA (32 KB / stage);
+//                              cp.async.bulk.tensor...cta_group::2 credits both CTAs' bytes to the
+//                              leader's mbarrier
+//   warp 1    MMA issuer       (leader CTA) tcgen05.mma.cta_group::2 kind::tf32 M=256 N=256 K=8; the 512
+//                              TMEM columns hold TWO accumulators so tile i+1's main loop overlaps tile
+//                              i's epilogue; tcgen05.commit...multicast::cluster frees a stage in both CTAs
+//   warps 2-9 epilogue         two warps per TMEM lane quarter (half of the columns each):
+//                              tcgen05.ld -> per-warp shared-memory transpose -> fused
+//                              bias / residual / erf-GELU / GELU' / column sums and fully coalesced
+//                              128-bit global loads/stores (each store instruction covers 4 complete
 //                              128-byte row segments)
 // Tiles are rasterised in groups of 2 m-tiles x all n-tiles, so the 74 pairs that run together read
 // few distinct A (activation) row blocks as well as few B (weight) tiles: the fp32-operand main loop
