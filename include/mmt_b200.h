@@ -65,7 +65,11 @@ enum { MMT_EPI_NONE = 0,
        MMT_EPI_DGELU = 2 }; /* C <- value * gelu_erf'(aux)   (autograd of bert.py:53)               */
 enum { MMT_GEMM_SPLIT_K = 1 };
 enum { MMT_PREC_FP32 = 0,   /* CUDA-core FMA, fp32 operands and accumulation (exact-order class)     */
-       MMT_PREC_TF32 = 1 }; /* tcgen05 kind::tf32 tensor-core tiles, TMA-fed, fp32 accumulate in TMEM */
+       MMT_PREC_TF32 = 1,   /* tcgen05 kind::tf32 tensor-core tiles, TMA-fed, fp32 accumulate in TMEM */
+       MMT_PREC_BF16 = 2 }; /* EXPERIMENTAL 16-bit operand mode: A and B point to bf16 data (K-major, strides
+                               in elements, un-batched, M >= 256), kind::f16 MMAs, fp32 C / epilogue operands.
+                               Not used by the train step (it cannot hold the 1e-3 bar); mmt_cast_bf16 makes
+                               the operand copies */
 
 typedef struct mmt_gemm_desc {
   int32_t M, N, K;
@@ -239,6 +243,10 @@ int mmt_max_margin_fwd_bwd(const float* x, int32_t n, float margin, int32_t fix_
 int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                   void* stream);
+
+/* fp32 -> bf16 (round to nearest even) copy of n elements, n % 4 == 0, 16-byte aligned buffers:
+ * operand producer of the experimental MMT_PREC_BF16 mode. */
+int mmt_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Retrieval ranks on the device (model/metric.py:26-150 t2v_metrics, :152-230 v2t_metrics): 0-based

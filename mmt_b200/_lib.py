@@ -19,7 +19,7 @@ c_u64 = ctypes.c_uint64
 c_p = ctypes.c_void_p
 
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 GEMM_SPLIT_K = 1
 
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "mmt_softmax_mask_bwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p]),
     "mmt_attention_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_u32, c_p, c_p, c_p, c_p,
                                   c_i32, c_p]),
+    "mmt_cast_bf16": (c_i32, [c_p, c_p, c_i64, c_p]),
     "mmt_retrieval_ranks": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p]),
     "mmt_readout_norm_fwd": (c_i32, [c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     "mmt_readout_norm_bwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p]),

@@ -36,6 +36,7 @@ int num_sms() {
 
 int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream);
 int gemm_tc(const mmt_gemm_desc& d, cudaStream_t stream);
+int gemm_tc_pair_bf16(const mmt_gemm_desc& d, cudaStream_t stream);
 
 }  // namespace mmt
 
@@ -68,10 +69,11 @@ int mmt_gemm(const mmt_gemm_desc* d, void* stream) {
   MMT_ARG_CHECK(d->epilogue == MMT_EPI_NONE || d->aux != nullptr, MMT_E_ARG,
                 "mmt_gemm: epilogue %d needs aux", d->epilogue);
   MMT_ARG_CHECK(d->batch <= 65535, MMT_E_SHAPE, "mmt_gemm: batch %d > 65535", d->batch);
-  MMT_ARG_CHECK(d->colsum == nullptr || d->precision == MMT_PREC_TF32, MMT_E_UNSUPPORTED,
-                "mmt_gemm: the fused column-sum epilogue exists on the MMT_PREC_TF32 path only");
+  MMT_ARG_CHECK(d->colsum == nullptr || d->precision != MMT_PREC_FP32, MMT_E_UNSUPPORTED,
+                "mmt_gemm: the fused column-sum epilogue exists on the tensor-core paths only");
   if (d->M == 0 || d->N == 0) return 0;
   if (d->precision == MMT_PREC_TF32) return mmt::gemm_tc(*d, (cudaStream_t)stream);
+  if (d->precision == MMT_PREC_BF16) return mmt::gemm_tc_pair_bf16(*d, (cudaStream_t)stream);
   MMT_ARG_CHECK(d->precision == MMT_PREC_FP32, MMT_E_ARG, "mmt_gemm: bad precision %d",
                 d->precision);
   return mmt::gemm_simt(*d, (cudaStream_t)stream);

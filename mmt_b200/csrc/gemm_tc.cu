@@ -317,6 +317,23 @@ int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t 
 }
 
 
+// bf16 operand [rows, K] contiguous along k (row pitch ld elements): rank-4 map (two unit batch dims) with
+// a {64 k, tile_rows} box and the 128-byte swizzle -- byte-for-byte the layout of the fp32 K-major box.
+int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int tile_rows, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled unavailable");
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 2) % 16 == 0 && ld >= 1, MMT_E_ALIGN,
+                "gemm_tc: bf16 operand %s needs a 16-byte aligned base and row pitch (ld=%lld)", what, (long long)ld);
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, 1, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2, (cuuint64_t)ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tile_rows, 1, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled(%s, bf16) failed with %d", what, (int)r);
+  return 0;
+}
+
 // Plain 2-D fp32 tensor map [rows, cols] (row pitch ld floats), box {box_cols, box_rows}.
 int make_tf32_map2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
                     int box_rows, bool atom32, const char* what) {

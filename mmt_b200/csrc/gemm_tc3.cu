@@ -65,6 +65,15 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t a_desc, 
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {       // arrives on `bar` in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
@@ -104,7 +113,10 @@ struct Tc3Args {
 };
 
 // Pair tile 256 (m) x 256 (n); per CTA and stage: A 128x32 + B 128x32 fp32 = 32 KB, 6 stages.
-template <bool A_MN, bool B_MN>
+// BF16 (experimental 16-bit operand mode, K-major operands only): the same 128-byte rows hold 64
+// bf16 instead of 32 fp32, one k-block is 64 k, one MMA (kind::f16) covers K = 16; staging, barriers,
+// TMEM use and the fp32 epilogue are unchanged.
+template <bool A_MN, bool B_MN, bool BF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const Tc3Args args) {
@@ -173,7 +185,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const int k0 = (kb0 + i) * BK;
+          const int k0 = (kb0 + i) * (BF16 ? 2 * BK : BK);      // elements: 128-byte rows either way
           const int ma = m0 + (int)rank * BM, nb_ = n0 + (int)rank * BNH;
           if (!A_MN) {
             tma_load_4d_2sm(sa, &map_a, &full_bar[s], k0, ma, z1, z0);
@@ -193,7 +205,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader) {
-      const uint32_t idesc = make_idesc_tf32(2 * BM, BN, A_MN, B_MN);     // M = 256 across the pair
+      static_assert(!BF16 || (!A_MN && !B_MN), "the bf16 mode takes K-major operands only");
+      const uint32_t idesc = BF16 ? make_idesc_bf16(2 * BM, BN, false, false)
+                                  : make_idesc_tf32(2 * BM, BN, A_MN, B_MN);     // M = 256 across the pair
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = A_MN ? 512 : 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
       constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = B_MN ? 512 : 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
       constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
@@ -217,7 +231,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * A_STEP, A_LBO, A_SBO, A_LT);
             const uint64_t db = make_smem_desc(sb + k * B_STEP, B_LBO, B_SBO, B_LT);
-            umma_tf32_2sm(acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (BF16) umma_bf16_2sm(acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else umma_tf32_2sm(acc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[s]);                    // frees the slot in both CTAs
         }
@@ -358,11 +373,11 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool BF16 = false>
 int launch3(const CUtensorMap& ma, const CUtensorMap& mb, const Tc3Args& args, cudaStream_t stream) {
   constexpr size_t smem = 5 * (A_BYTES + 128 * BK * 4) + EPI_WARPS * STG_BYTES_PER_WARP + 1024 + 256;
   static bool configured = false;
-  auto kern = gemm_tc3_kernel<A_MN, B_MN>;
+  auto kern = gemm_tc3_kernel<A_MN, B_MN, BF16>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc3 smem attribute");
@@ -422,6 +437,31 @@ int gemm_tc_pair(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken) {
   if (!a_mn && b_mn) return launch3<false, true>(ma, mb, args, stream);
   if (a_mn && !b_mn) return launch3<true, false>(ma, mb, args, stream);
   return launch3<true, true>(ma, mb, args, stream);
+}
+
+// Experimental: C = epilogue(alpha * A B^T ...) with bf16 operands A [M, K], B [N, K] (both K-major,
+// d.A / d.B point to bf16 data, strides in elements), fp32 C and epilogue operands.  CTA-pair kernel only.
+int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int tile_rows, const char* what);
+
+int gemm_tc_pair_bf16(const mmt_gemm_desc& d, cudaStream_t stream) {
+  MMT_ARG_CHECK(d.batch == 1 && d.c_mb == 0 && d.a_kb == 0 && d.a_ks == 1 && d.b_ks == 1, MMT_E_UNSUPPORTED,
+                "mmt_gemm(bf16): un-batched K-major operands only");
+  MMT_ARG_CHECK(d.M >= 256 && d.N >= 128 && d.K >= 64, MMT_E_UNSUPPORTED, "mmt_gemm(bf16): problem too small (M=%d N=%d K=%d)", d.M, d.N, d.K);
+  MMT_ARG_CHECK(d.colsum == nullptr || true, MMT_E_UNSUPPORTED, "unused");
+  Tc3Args args;
+  args.d = d;                                             // bf16 x bf16 products are exact in fp32: no compensation
+  args.num_m_tiles = (d.M + 2 * BM - 1) / (2 * BM);
+  args.num_n_tiles = (d.N + 255) / 256;
+  args.num_kb = (d.K + 63) / 64;
+  args.split_k = 1;
+  args.kb_per_split = args.num_kb;
+  args.group_m = 2 < args.num_m_tiles ? 2 : args.num_m_tiles;
+  CUtensorMap ma, mb;
+  int rc = make_bf16_map(&ma, d.A, d.M, d.K, d.a_ms, BM, "A");
+  if (rc) return rc;
+  rc = make_bf16_map(&mb, d.B, d.N, d.K, d.b_ns, 128, "B");
+  if (rc) return rc;
+  return launch3<false, false, true>(ma, mb, args, stream);
 }
 
 }  // namespace mmt

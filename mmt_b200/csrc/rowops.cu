@@ -523,6 +523,19 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
   }
 }
 
+// fp32 -> bf16 round-to-nearest-even, 4 elements per thread (operands of the experimental MMT_PREC_BF16 GEMM)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4) {
+  pdl_trigger();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    uint32_t lo, hi;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));     // d = {hi: first src, lo: second src}
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+    out[i] = make_uint2(lo, hi);
+  }
+}
+
 }  // namespace
 }  // namespace mmt
 
@@ -674,6 +687,19 @@ int mmt_dropout(const float* in, float* out, int64_t rows, int32_t n, float p, u
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   launch_pdl(dropout_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, in, out, rows, n / 4, p, seed, site, g_step_ctr);
   MMT_LAUNCH_CHECK("dropout");
+  return 0;
+}
+
+int mmt_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  MMT_ARG_CHECK(in && out_bf16, MMT_E_ARG, "mmt_cast_bf16: null pointer");
+  MMT_ARG_CHECK(n >= 0 && (n & 3) == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out_bf16 % 8) == 0, MMT_E_ALIGN,
+                "mmt_cast_bf16: n must be a multiple of 4 and the buffers aligned");
+  if (n == 0) return 0;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  launch_pdl(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(in),
+             reinterpret_cast<uint2*>(out_bf16), n / 4);
+  MMT_LAUNCH_CHECK("cast_bf16");
   return 0;
 }
 

@@ -122,5 +122,11 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, bool a_mn, boo
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f16 with bf16 operands (a_format = b_format = 1), fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 }  // namespace tc
 }  // namespace mmt

@@ -813,3 +813,30 @@ def test_retrieval_metrics_on_gpu_match_reference_golden_and_oracle(dev, golden_
     r_v2t = metric.retrieval_ranks(big, m, v2t=True)
     assert np.array_equal(r_t2v, O.retrieval_ranks(big))
     assert np.array_equal(r_v2t, O.retrieval_ranks_v2t(big, m))
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 384, 320), (1000, 520, 200), (2048, 3072, 512)])
+def test_gemm_bf16_operand_mode_experimental(dev, M, N, K):
+  """MMT_PREC_BF16 (experimental): bf16 K-major operands made by mmt_cast_bf16, kind::f16 MMAs on the
+  CTA-pair kernel, fp32 accumulate and epilogue.  Products of bf16 values are exact in fp32, so against
+  an fp64 product of the ROUNDED operands only the accumulation order differs."""
+  from mmt_b200 import _lib
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(K)
+  A = torch.randn(M, K, generator=g).to(dev)
+  W = (torch.randn(N, K, generator=g) * 0.05).to(dev)
+  bias = torch.randn(N, generator=g).to(dev)
+  Ab = torch.empty(M, K, dtype=torch.bfloat16, device=dev)
+  Wb = torch.empty(N, K, dtype=torch.bfloat16, device=dev)
+  _lib.check(lib.mmt_cast_bf16(_lib.ptr(A), _lib.ptr(Ab), M * K, _lib.stream_ptr()), "cast")
+  _lib.check(lib.mmt_cast_bf16(_lib.ptr(W), _lib.ptr(Wb), N * K, _lib.stream_ptr()), "cast")
+  torch.cuda.synchronize()
+  assert torch.equal(Ab, A.to(torch.bfloat16)) and torch.equal(Wb, W.to(torch.bfloat16))   # round to nearest even
+  C = torch.full((M, N), float("nan"), device=dev)
+  u = torch.empty(M, N, device=dev)
+  _lib.gemm(M, N, K, Ab, K, 1, Wb, K, 1, C, N, bias=bias, precision=_lib.PREC_BF16)
+  ref = Ab.double() @ Wb.double().t() + bias.double()
+  assert torch.isfinite(C).all()
+  assert H.rel_err(C, ref) < 2e-6
+  _lib.gemm(M, N, K, Ab, K, 1, Wb, K, 1, C, N, bias=bias, epilogue=_lib.EPI_GELU, aux=u, precision=_lib.PREC_BF16)
+  assert H.rel_err(u, ref) < 2e-6 and H.rel_err(C, O.gelu(ref)) < 2e-5

@@ -33,3 +33,17 @@ for name, N, K, epi, has_add in CASES:
   ref = (A @ W.t() + bias + (add if add is not None else 0)) if epi == _lib.EPI_NONE else None
   err = float((C - ref).abs().max() / ref.abs().max()) if ref is not None else float("nan")
   print("%-14s M=%d N=%4d K=%4d  %7.1f us  %6.1f TFLOP/s  err %.1e" % (name, M, N, K, us, 2.0 * M * N * K / us * 1e-6, err))
+  if os.environ.get("MMT_BENCH_BF16", "1") != "0":           # experimental 16-bit operand mode, same shape
+    Ab, Wb = A.to(torch.bfloat16), W.to(torch.bfloat16)
+    def run16():
+      _lib.gemm(M, N, K, Ab, K, 1, Wb, K, 1, C, N, bias=bias, add=add, aux=aux, epilogue=epi, precision=_lib.PREC_BF16)
+    for _ in range(3): run16()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters): run16()
+    e1.record(); torch.cuda.synchronize()
+    us16 = e0.elapsed_time(e1) * 1e3 / iters
+    ref16 = (Ab.double() @ Wb.double().t() + bias.double() + (add.double() if add is not None else 0)) if epi == _lib.EPI_NONE else None
+    err16 = float((C.double() - ref16).abs().max() / ref16.abs().max()) if ref16 is not None else float("nan")
+    print("%-14s   bf16 operands     %7.1f us  %6.1f TFLOP/s  err %.1e (vs fp64 product of the rounded operands)" %
+          ("", us16, 2.0 * M * N * K / us16 * 1e-6, err16))
