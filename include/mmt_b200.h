@@ -66,8 +66,9 @@ enum { MMT_EPI_NONE = 0,
 enum { MMT_GEMM_SPLIT_K = 1 };
 enum { MMT_PREC_FP32 = 0,   /* CUDA-core FMA, fp32 operands and accumulation (exact-order class)     */
        MMT_PREC_TF32 = 1,   /* tcgen05 kind::tf32 tensor-core tiles, TMA-fed, fp32 accumulate in TMEM */
-       MMT_PREC_BF16 = 2 }; /* EXPERIMENTAL 16-bit operand mode: A and B point to bf16 data (K-major, strides
-                               in elements, un-batched, M >= 256), kind::f16 MMAs, fp32 C / epilogue operands.
+       MMT_PREC_BF16 = 2 }; /* EXPERIMENTAL 16-bit operand mode: A and B point to bf16 data (strides in elements,
+                               contiguous along k or along m / n, un-batched, M >= 256), kind::f16 MMAs, fp32 C /
+                               epilogue operands.
                                Not used by the train step (it cannot hold the 1e-3 bar); mmt_cast_bf16 makes
                                the operand copies */
 

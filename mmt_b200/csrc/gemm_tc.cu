@@ -317,16 +317,18 @@ int make_tf32_map(CUtensorMap* map, const float* base, int rows, int K, int64_t 
 }
 
 
-// bf16 operand [rows, K] contiguous along k (row pitch ld elements): rank-4 map (two unit batch dims) with
-// a {64 k, tile_rows} box and the 128-byte swizzle -- byte-for-byte the layout of the fp32 K-major box.
-int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int tile_rows, const char* what) {
+// bf16 operand of `rows` x K: rank-4 map (two unit batch dims) with the 128-byte swizzle.  K-major (row
+// pitch ld elements): box {64 k, tile_rows} -- byte-for-byte the layout of the fp32 K-major box.  MN-major
+// (element (r, k) at k * ld + r): box {64 rows, 64 k}.
+int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, bool mn_major, int tile_rows,
+                  const char* what) {
   EncodeTiledFn enc = get_encode();
   MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "gemm_tc: cuTensorMapEncodeTiled unavailable");
   MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 2) % 16 == 0 && ld >= 1, MMT_E_ALIGN,
-                "gemm_tc: bf16 operand %s needs a 16-byte aligned base and row pitch (ld=%lld)", what, (long long)ld);
-  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, 1, 1};
+                "gemm_tc: bf16 operand %s needs a 16-byte aligned base and pitch (ld=%lld)", what, (long long)ld);
+  cuuint64_t dims[4] = {(cuuint64_t)(mn_major ? rows : K), (cuuint64_t)(mn_major ? K : rows), 1, 1};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2, (cuuint64_t)ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)tile_rows, 1, 1}, estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(mn_major ? 64 : tile_rows), 1, 1}, estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -113,9 +113,9 @@ struct Tc3Args {
 };
 
 // Pair tile 256 (m) x 256 (n); per CTA and stage: A 128x32 + B 128x32 fp32 = 32 KB, 6 stages.
-// BF16 (experimental 16-bit operand mode, K-major operands only): the same 128-byte rows hold 64
-// bf16 instead of 32 fp32, one k-block is 64 k, one MMA (kind::f16) covers K = 16; staging, barriers,
-// TMEM use and the fp32 epilogue are unchanged.
+// BF16 (experimental 16-bit operand mode): the same 128-byte rows hold 64 bf16 instead of 32 fp32, one
+// k-block is 64 k, one MMA (kind::f16) covers K = 16; staging, barriers, TMEM use and the fp32 epilogue
+// are unchanged.
 template <bool A_MN, bool B_MN, bool BF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -187,17 +187,19 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* sb = sa + A_BYTES;
           const int k0 = (kb0 + i) * (BF16 ? 2 * BK : BK);      // elements: 128-byte rows either way
           const int ma = m0 + (int)rank * BM, nb_ = n0 + (int)rank * BNH;
+          // MN-major operands arrive as boxes of one 128-byte row of MNW elements x KR k-rows
+          constexpr int MNW = BF16 ? 64 : 32, KR = BF16 ? 64 : 32;
           if (!A_MN) {
             tma_load_4d_2sm(sa, &map_a, &full_bar[s], k0, ma, z1, z0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j) tma_load_4d_2sm(sa + j * (BK * 128), &map_a, &full_bar[s], ma + 32 * j, k0, z1, z0);
+            for (int j = 0; j < BM / MNW; ++j) tma_load_4d_2sm(sa + j * (KR * 128), &map_a, &full_bar[s], ma + MNW * j, k0, z1, z0);
           }
           if (!B_MN) {
             tma_load_4d_2sm(sb, &map_b, &full_bar[s], k0, nb_, z1, z0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BNH / 32; ++j) tma_load_4d_2sm(sb + j * (BK * 128), &map_b, &full_bar[s], nb_ + 32 * j, k0, z1, z0);
+            for (int j = 0; j < BNH / MNW; ++j) tma_load_4d_2sm(sb + j * (KR * 128), &map_b, &full_bar[s], nb_ + MNW * j, k0, z1, z0);
           }
         }
       }
@@ -205,12 +207,17 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && leader) {
-      static_assert(!BF16 || (!A_MN && !B_MN), "the bf16 mode takes K-major operands only");
-      const uint32_t idesc = BF16 ? make_idesc_bf16(2 * BM, BN, false, false)
+      const uint32_t idesc = BF16 ? make_idesc_bf16(2 * BM, BN, A_MN, B_MN)
                                   : make_idesc_tf32(2 * BM, BN, A_MN, B_MN);     // M = 256 across the pair
-      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_SBO = A_MN ? 512 : 1024, A_STEP = A_MN ? 1024 : UMMA_K * 4;
-      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_SBO = B_MN ? 512 : 1024, B_STEP = B_MN ? 1024 : UMMA_K * 4;
-      constexpr uint32_t A_LT = A_MN ? 1 : 2, B_LT = B_MN ? 1 : 2;
+      // MN-major operands.  tf32: 32-byte-atom swizzle (layout 1): 4-k-row groups 512 B apart (SBO), MN chunks
+      // of 32 one box (32 k-rows x 128 B) apart (LBO), 8 k per MMA = 1024 B.  bf16: plain 128-byte swizzle
+      // (layout 2): 8-k-row atoms 1024 B apart (SBO), MN chunks of 64 one box (64 k-rows x 128 B) apart (LBO),
+      // 16 k per MMA = 2048 B.
+      constexpr uint32_t MN_LBO = BF16 ? 64 * 128 : BK * 128, MN_SBO = BF16 ? 1024 : 512, MN_STEP = BF16 ? 2048 : 1024;
+      constexpr uint32_t MN_LT = BF16 ? 2 : 1;
+      constexpr uint32_t A_LBO = A_MN ? MN_LBO : 16, A_SBO = A_MN ? MN_SBO : 1024, A_STEP = A_MN ? MN_STEP : UMMA_K * 4;
+      constexpr uint32_t B_LBO = B_MN ? MN_LBO : 16, B_SBO = B_MN ? MN_SBO : 1024, B_STEP = B_MN ? MN_STEP : UMMA_K * 4;
+      constexpr uint32_t A_LT = A_MN ? MN_LT : 2, B_LT = B_MN ? MN_LT : 2;
       uint32_t g = 0;
       int it = 0;
       for (int w = pair_id; w < num_work; w += num_pairs, ++it) {
@@ -439,15 +446,18 @@ int gemm_tc_pair(const mmt_gemm_desc& d, cudaStream_t stream, bool* taken) {
   return launch3<true, true>(ma, mb, args, stream);
 }
 
-// Experimental: C = epilogue(alpha * A B^T ...) with bf16 operands A [M, K], B [N, K] (both K-major,
-// d.A / d.B point to bf16 data, strides in elements), fp32 C and epilogue operands.  CTA-pair kernel only.
-int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, int tile_rows, const char* what);
+// Experimental: C = epilogue(alpha * A B^T ...) with bf16 operands (d.A / d.B point to bf16 data, strides in
+// elements, each contiguous along k or along m / n), fp32 C and epilogue operands.  CTA-pair kernel only.
+int make_bf16_map(CUtensorMap* map, const void* base, int rows, int K, int64_t ld, bool mn_major, int tile_rows,
+                  const char* what);
 
 int gemm_tc_pair_bf16(const mmt_gemm_desc& d, cudaStream_t stream) {
-  MMT_ARG_CHECK(d.batch == 1 && d.c_mb == 0 && d.a_kb == 0 && d.a_ks == 1 && d.b_ks == 1, MMT_E_UNSUPPORTED,
-                "mmt_gemm(bf16): un-batched K-major operands only");
+  MMT_ARG_CHECK(d.batch == 1 && d.c_mb == 0 && d.a_kb == 0, MMT_E_UNSUPPORTED, "mmt_gemm(bf16): un-batched operands only");
+  const bool a_mn = (d.a_ks != 1), b_mn = (d.b_ks != 1);
+  MMT_ARG_CHECK((!a_mn || d.a_ms == 1) && (!b_mn || d.b_ns == 1), MMT_E_UNSUPPORTED,
+                "mmt_gemm(bf16): operands must be contiguous along k or along m / n");
   MMT_ARG_CHECK(d.M >= 256 && d.N >= 128 && d.K >= 64, MMT_E_UNSUPPORTED, "mmt_gemm(bf16): problem too small (M=%d N=%d K=%d)", d.M, d.N, d.K);
-  MMT_ARG_CHECK(d.colsum == nullptr || true, MMT_E_UNSUPPORTED, "unused");
+  MMT_ARG_CHECK(!(d.flags & MMT_GEMM_SPLIT_K), MMT_E_UNSUPPORTED, "mmt_gemm(bf16): split-K is not wired up");
   Tc3Args args;
   args.d = d;                                             // bf16 x bf16 products are exact in fp32: no compensation
   args.num_m_tiles = (d.M + 2 * BM - 1) / (2 * BM);
@@ -457,11 +467,14 @@ int gemm_tc_pair_bf16(const mmt_gemm_desc& d, cudaStream_t stream) {
   args.kb_per_split = args.num_kb;
   args.group_m = 2 < args.num_m_tiles ? 2 : args.num_m_tiles;
   CUtensorMap ma, mb;
-  int rc = make_bf16_map(&ma, d.A, d.M, d.K, d.a_ms, BM, "A");
+  int rc = make_bf16_map(&ma, d.A, d.M, d.K, a_mn ? d.a_ks : d.a_ms, a_mn, BM, "A");
   if (rc) return rc;
-  rc = make_bf16_map(&mb, d.B, d.N, d.K, d.b_ns, 128, "B");
+  rc = make_bf16_map(&mb, d.B, d.N, d.K, b_mn ? d.b_ks : d.b_ns, b_mn, 128, "B");
   if (rc) return rc;
-  return launch3<false, false, true>(ma, mb, args, stream);
+  if (!a_mn && !b_mn) return launch3<false, false, true>(ma, mb, args, stream);
+  if (!a_mn && b_mn) return launch3<false, true, true>(ma, mb, args, stream);
+  if (a_mn && !b_mn) return launch3<true, false, true>(ma, mb, args, stream);
+  return launch3<true, true, true>(ma, mb, args, stream);
 }
 
 }  // namespace mmt

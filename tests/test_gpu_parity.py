@@ -840,3 +840,11 @@ def test_gemm_bf16_operand_mode_experimental(dev, M, N, K):
   assert H.rel_err(C, ref) < 2e-6
   _lib.gemm(M, N, K, Ab, K, 1, Wb, K, 1, C, N, bias=bias, epilogue=_lib.EPI_GELU, aux=u, precision=_lib.PREC_BF16)
   assert H.rel_err(u, ref) < 2e-6 and H.rel_err(C, O.gelu(ref)) < 2e-5
+  # operands contiguous along m / n (what dgrad and wgrad products need): all four combinations
+  if M % 8 == 0 and N % 8 == 0:
+    At, Wt = Ab.t().contiguous(), Wb.t().contiguous()          # [K, M], [K, N]
+    for a_t, w_t in ((False, True), (True, False), (True, True)):
+      C.fill_(float("nan"))
+      _lib.gemm(M, N, K, At if a_t else Ab, 1 if a_t else K, M if a_t else 1, Wt if w_t else Wb,
+                1 if w_t else K, N if w_t else 1, C, N, bias=bias, precision=_lib.PREC_BF16)
+      assert H.rel_err(C, ref) < 2e-6, (a_t, w_t)
