@@ -272,3 +272,48 @@ def test_grad_reducer_covers_the_buffer_exactly_once():
       red.finish()
   finally:
     parallel.dist = real
+
+
+def test_data_parallel_gradient_pieces_partition_the_real_layout():
+  """The pieces the data-parallel backward exchanges (head matrices early, one block per encoder layer, the
+  rest at the end; the pooler skipped) cover the real flat layout exactly once."""
+  import mmt_test_helpers as H
+  from mmt_b200 import parallel
+  from mmt_b200.params import Layout
+  ed, vb, P, batch, cfg = H.make_case(["face", "ocr", "rgb", "s3d", "scene", "speech", "vggish"], 2, 30)
+  L = Layout(ed, vb, 768, 512)
+  pieces = [(o, n) for o, n in parallel.head_segments(L) if o >= L.small_numel]
+  pieces += [L.layer_big_range(l) for l in range(L.L)]
+  skipped = L.no_grad_ranges()
+  covered = sorted(pieces + skipped)
+  pos, rest = 0, []
+  for o, n in covered + [(L.numel, 0)]:
+    assert o >= pos, "overlapping pieces"
+    if o > pos:
+      rest.append((pos, o - pos))
+    pos = o + n
+  assert len(rest) == 1 and rest[0][0] == 0            # ONE remainder piece: small region + ReduceDim weights
+  assert rest[0][1] == L.layer_big_range(0)[0]
+  # every trainable parameter lies inside exactly one exchanged piece
+  for name, seg in L.segments.items():
+    if name.startswith("vid_bert.pooler.dense.weight"):
+      continue
+    inside = [1 for o, n in pieces + rest if o <= seg.offset and seg.offset + seg.numel <= o + n]
+    assert len(inside) == 1, name
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line with the
+  contract's keys; smallest workload so the test stays in seconds."""
+  import json
+  import subprocess
+  import sys
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1",
+                      "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+  assert r.returncode == 0, r.stderr[-2000:]
+  line = json.loads(r.stdout.strip().splitlines()[-1])
+  for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+            "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+    assert k in line, k
+  assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+  assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
