@@ -317,3 +317,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert k in line, k
   assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
   assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="needs the reference checkout")
+def test_integration_shim_package_overrides_three_modules_and_keeps_the_rest():
+  """integration/model ahead of the reference on sys.path: model.model / model.loss / model.metric are
+  the B200 surface, any other submodule (here model.bert) is the reference's own file."""
+  import subprocess
+  import sys
+  code = (
+      "import model, model.model, model.loss, model.metric, model.bert\n"
+      "import mmt_b200.model.model as mm, mmt_b200.model.loss as ml, mmt_b200.model.metric as mt\n"
+      "assert model.model.CENet is mm.CENet\n"
+      "assert model.model.sharded_cross_view_inner_product is mm.sharded_cross_view_inner_product\n"
+      "assert model.loss.MaxMarginRankingLoss is ml.MaxMarginRankingLoss\n"
+      "assert model.metric.t2v_metrics is mt.t2v_metrics and model.metric.v2t_metrics is mt.v2t_metrics\n"
+      "assert model.bert.__file__.startswith('/root/reference/model/'), model.bert.__file__\n"
+      "assert hasattr(model.bert, 'BertModel')\n"
+      "print('shim ok')\n")
+  env = dict(os.environ, MMT_REFERENCE_ROOT="/root/reference",
+             PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "integration"), ROOT]))
+  r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300, cwd="/tmp")
+  assert r.returncode == 0 and "shim ok" in r.stdout, r.stderr[-2000:]
