@@ -190,7 +190,8 @@ def run_b200(args):
                                "attention_probs_dropout_prob": DROPOUT}, txt_bert=feed)
   net.load_state_dict(P, strict=True)
   net.to(dev).train()
-  net.cfg.precision = _lib.PREC_TF32 if args.precision == "tf32" else _lib.PREC_FP32
+  net.cfg.precision = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16,
+                       "bf16": _lib.PREC_BF16}[args.precision]
   if world > 1:
     net.enable_data_parallel()
   crit = MaxMarginRankingLoss(margin=0.05, fix_norm=True)
@@ -372,7 +373,7 @@ def run_b200(args):
   res = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
       "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+      "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16", "bf16": "bf16"}[args.precision],
       "data": "synthetic",
       "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": B * world,
                  "scope": "hot path only: text encoder replaced by fixed [B,768] CLS features on both arms",
@@ -421,15 +422,29 @@ def roofline_ffn(net, w, B, dev, args):
   BS, d, ff = B * S, 512, 3072
   L = net.layout
   reps = 6
-  a = [torch.randn(BS, d, device=dev) for _ in range(reps)]
-  f = [torch.empty(BS, ff, device=dev) for _ in range(reps)]
-  u = [torch.empty(BS, ff, device=dev) for _ in range(reps)]
   p = "vid_bert.encoder.layer.0."
+  is16 = _lib.is16(net.cfg.precision)
+  if is16:
+    dt = _lib.dt_of(net.cfg.precision)
+    tdt = _lib.torch_dtype(dt)
+    net._prepare16()
+    a = [torch.randn(BS, d, device=dev).to(tdt) for _ in range(reps)]
+    f = [torch.empty(BS, ff, device=dev, dtype=tdt) for _ in range(reps)]
+    u = [torch.empty(BS, ff, device=dev, dtype=tdt) for _ in range(reps)]
 
-  def launch(i):
-    _lib.gemm(BS, ff, d, a[i], d, 1, net.flat, d, 1, f[i], ff, b_off=L.off(p + "intermediate.dense.weight"),
-              bias=net.flat, bias_off=L.off(p + "intermediate.dense.bias"), epilogue=_lib.EPI_GELU,
-              aux=u[i], precision=net.cfg.precision)
+    def launch(i):
+      _lib.gemm16(dt, BS, ff, d, a[i], d, 0, net.cfg.w16.flat16, d, 0, b_off=L.off(p + "intermediate.dense.weight"),
+                  bias=net.flat, bias_off=L.off(p + "intermediate.dense.bias"), epilogue=_lib.EPI_GELU, aux16=u[i],
+                  aux_ld=ff, C16=f[i], c16_ld=ff)
+  else:
+    a = [torch.randn(BS, d, device=dev) for _ in range(reps)]
+    f = [torch.empty(BS, ff, device=dev) for _ in range(reps)]
+    u = [torch.empty(BS, ff, device=dev) for _ in range(reps)]
+
+    def launch(i):
+      _lib.gemm(BS, ff, d, a[i], d, 1, net.flat, d, 1, f[i], ff, b_off=L.off(p + "intermediate.dense.weight"),
+                bias=net.flat, bias_off=L.off(p + "intermediate.dense.bias"), epilogue=_lib.EPI_GELU,
+                aux=u[i], precision=net.cfg.precision)
 
   for i in range(3):
     launch(i % reps)
@@ -607,8 +622,11 @@ def main():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-  ap.add_argument("--precision", default=os.environ.get("MMT_PRECISION", "tf32"),
-                  choices=["fp32", "tf32"])
+  ap.add_argument("--precision", default=os.environ.get("MMT_PRECISION", "f16"),
+                  choices=["fp32", "tf32", "f16", "bf16"],
+                  help="operand precision of the GEMMs / attention (accumulation, statistics, residuals, gradients "
+                       "are fp32 in every mode): f16 = fp16 operands (default; tf32's mantissa at half the bytes), "
+                       "bf16 (BASELINE config 5), tf32, fp32 = CUDA-core exact mode")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--graph", action="store_true",
                   help="replay the step as one CUDA graph for `value` (mmt_b200/graph.py); measured gain on "

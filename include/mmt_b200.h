@@ -260,6 +260,113 @@ int mmt_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 int mmt_retrieval_ranks(const float* sims, const int32_t* valid, int32_t Nq, int32_t Nv, int32_t v2t,
                         float* ranks, void* stream);
 
+/* =============================================================================================
+ * 16-bit operand path (the train step's default).  Every dense product of the step takes fp16 (or,
+ * for BASELINE config 5, bf16) operands that their PRODUCERS wrote with round-to-nearest-even
+ * conversion, accumulates in fp32 in TMEM and writes fp32 and / or 16-bit results.  fp16 has tf32's
+ * 10-bit mantissa at half the bytes; gradients travel in 16-bit tensors multiplied by a power-of-two
+ * `scale16` that the consuming GEMM's alpha divides out again (fp16 range), statistics, residual
+ * streams, parameter gradients and the loss stay fp32.
+ * `seed_ctr` (may be NULL): device-resident uint64 added to `seed` by the kernel, so a recorded
+ * launch sequence / CUDA graph draws fresh dropout masks on every replay.
+ * ============================================================================================= */
+enum { MMT_DT_F16 = 0, MMT_DT_BF16 = 1 };
+
+/* C(m,n) = epilogue(alpha * sum_k A(m,k) B(n,k)) with 16-bit A, B:
+ *   v = alpha*acc + bias[n];  GELU: aux16 <- v, v = gelu_erf(v);  DGELU: v *= gelu_erf'(aux16);
+ *   v *= dropout_mask(seed, site, m, n/4) / (1-p);  v += add(m,n);
+ *   C32 <- v;  C16 <- rn16(v * out16_scale);  colsum[n] += colsum_scale * sum_m v.
+ * A(m,k) = A[m*a_ld + k] (a_mn = 0) or A[k*a_ld + m] (a_mn = 1, "MN-major": dgrad / wgrad operands are
+ * read in place, nothing is transposed in HBM); B likewise.  Pitches and batch strides are in ELEMENTS
+ * and must be multiples of 8 (16 bytes); bases 16-byte aligned.  C32, C16, add and aux16 share the row
+ * index m, their own pitches, and the batch offsets z0*c_bs0 + z1*c_bs1 (elements).
+ * MMT_GEMM_SPLIT_K: plain fp32 C32 only; (tile, k-range) work items reduced with fp32 atomics.
+ * Replaces the same reference lines as mmt_gemm (model/bert.py:137-143,186,218,234; model/model.py:
+ * 698,723-726,746,277-279 and their autograd products). */
+typedef struct mmt_gemm16_desc {
+  int32_t M, N, K, dtype;
+  const void* A; int64_t a_ld; int32_t a_mn;
+  const void* B; int64_t b_ld; int32_t b_mn;
+  float* C32; int64_t c32_ld;
+  void* C16; int64_t c16_ld; float out16_scale;
+  const float* bias;
+  const float* add; int64_t add_ld;
+  void* aux16; int64_t aux_ld;
+  int32_t epilogue; float alpha;
+  float p_drop; uint32_t site; uint64_t seed; const uint64_t* seed_ctr;
+  int32_t batch, batch_inner;
+  int64_t a_bs0, a_bs1, b_bs0, b_bs1, c_bs0, c_bs1, bias_bs;
+  float* colsum; float colsum_scale; int64_t colsum_bs;
+  int32_t flags;
+} mmt_gemm16_desc;
+int mmt_gemm16(const mmt_gemm16_desc* d, void* stream);
+
+/* out[r, c] = rn16(mask * in[r*in_ld + c] * scale) for c < cols, 0 for cols <= c < out_cols (row pitch out_ld
+ * elements).  p_drop > 0 applies the (seed, site, r, c/4) dropout mask of mmt_dropout (moe_txt_dropout,
+ * model/model.py:274).  The per-step weight copy (rows = 1) and every small fp32 -> 16-bit operand copy. */
+int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, int32_t out_cols,
+               int64_t out_ld, float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
+               int32_t dtype, void* stream);
+
+/* ReduceDim operands (model/model.py:426-437): per expert k the max-pooled row and the T frame rows are
+ * packed as one 16-bit [B, T+1, ld[k]] matrix (row 0 = maxpool = the [AGG] token's input), columns
+ * in[k]..ld[k] zero -- ONE launch for all experts (replaces M torch.cat + M casts). */
+#define MMT_MAX_EXPERTS 16
+typedef struct mmt_pack_desc {
+  const float* feats[MMT_MAX_EXPERTS];   /* [B, T, in[k]] */
+  const float* maxp[MMT_MAX_EXPERTS];    /* [B, in[k]] */
+  void* out[MMT_MAX_EXPERTS];            /* [B, T+1, ld[k]] 16-bit */
+  int32_t in[MMT_MAX_EXPERTS], ld[MMT_MAX_EXPERTS];
+  int32_t n, B, T, dtype;
+} mmt_pack_desc;
+int mmt_pack_inputs16(const mmt_pack_desc* d, void* stream);
+
+/* mmt_embed_ln_fwd that additionally writes h16 [B*S, d] = rn16(h) (the QKV GEMM's operand). */
+int mmt_embed_ln16_fwd(const float* proj, const float* ft, const float* ind, const int32_t* type_idx,
+                       const float* pos_emb, const float* type_emb, const float* gamma, const float* beta,
+                       int32_t B, int32_t M, int32_t T, int32_t d, int32_t max_pos, float eps, float p_drop,
+                       uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* h, void* h16, float* mask,
+                       int32_t* pos_ids, int32_t* type_ids, float* inv_norm, float* mean, float* rstd,
+                       int32_t dtype, void* stream);
+/* mmt_embed_ln_bwd that additionally writes dproj16 = rn16(dproj * scale16) (ReduceDim wgrad operand). */
+int mmt_embed_ln16_bwd(const float* dh, const float* proj, const int32_t* pos_ids, const int32_t* type_ids,
+                       const float* inv_norm, const float* mean, const float* rstd, const float* pos_emb,
+                       const float* type_emb, const float* gamma, int32_t B, int32_t M, int32_t T, int32_t d,
+                       float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* dproj,
+                       void* dproj16, float scale16, float* dpos_emb, float* dtype_emb, float* dgamma,
+                       float* dbeta, int32_t dtype, void* stream);
+
+/* y = LayerNorm(z) (model/bert.py:188, 236) where z = dropout(dense) + residual was written by the GEMM
+ * epilogue; writes y (fp32, the next residual) and y16 (the next GEMM operand), saves mean / rstd. */
+int mmt_ln16_fwd(const float* z, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
+                 float* y, void* y16, float* mean, float* rstd, int32_t dtype, void* stream);
+/* dz = LN'(dy (+ dy2)) in fp32 (the residual branch's gradient); dt16 = rn16(dropout_mask * dz * scale16)
+ * (the dense layer's output gradient: operand of its dgrad / wgrad GEMMs); ACCUMULATES dgamma, dbeta and
+ * dbias (= column sums of mask * dz). */
+int mmt_ln16_bwd(const float* dy, const float* dy2, const float* z, const float* mean, const float* rstd,
+                 const float* gamma, int64_t rows, int32_t d, float p_drop, uint64_t seed,
+                 const uint64_t* seed_ctr, uint32_t site, float* dz, void* dt16, float scale16, float* dgamma,
+                 float* dbeta, float* dbias, int32_t dtype, void* stream);
+
+/* Fused self-attention (model/bert.py:136-172) on 16-bit operands, nothing of size S x S in HBM:
+ * forward  ctx16[b,i,h*dh:(h+1)*dh] = dropout(softmax(Q K^T * scale + (1-mask) * -10000)) V, lse [B,H,S];
+ * backward recomputes the probabilities from qkv16 and lse (the Philox mask from (seed, site)) and writes
+ *          dqkv16 = scale16-domain gradients of Q | K | V (same layout as qkv16), accumulating the QKV bias
+ *          gradient dbias [3*H*dh] (fp32, divided by scale16).  dctx16 carries scale16 already.
+ * dh must be 128, d = H*dh.  dq32 is a zeroed fp32 workspace [B*S, H*dh] the kernel accumulates dQ in. */
+int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t B, int32_t H, int32_t S, int32_t dh,
+                        float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
+                        void* ctx16, float* lse, int32_t dtype, void* stream);
+int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const void* dctx16, const float* lse,
+                        const float* mask, int32_t B, int32_t H, int32_t S, int32_t dh, float scale, float p_drop,
+                        uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float scale16, void* dqkv16,
+                        float* dq32, float* delta, float* dbias, int32_t dtype, void* stream);
+
+/* Adam that also refreshes the 16-bit weight copy: p16[i] = rn16(p[i]) after the update (p16 may be NULL). */
+int mmt_adam16_step(float* p, const float* g, float* m, float* v, void* p16, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, const uint64_t* step_ctr,
+                    float grad_scale, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

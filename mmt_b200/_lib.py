@@ -19,8 +19,22 @@ c_u64 = ctypes.c_uint64
 c_p = ctypes.c_void_p
 
 EPI_NONE, EPI_GELU, EPI_DGELU = 0, 1, 2
-PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_F16 = 0, 1, 2, 3     # engine-level precision of the train step
 GEMM_SPLIT_K = 1
+DT_F16, DT_BF16 = 0, 1
+MAX_EXPERTS = 16
+
+
+def is16(precision):
+  return precision in (PREC_F16, PREC_BF16)
+
+
+def dt_of(precision):
+  return DT_BF16 if precision == PREC_BF16 else DT_F16
+
+
+def torch_dtype(dt):
+  return torch.bfloat16 if dt == DT_BF16 else torch.float16
 
 
 class GemmDesc(ctypes.Structure):
@@ -38,6 +52,34 @@ class GemmDesc(ctypes.Structure):
       ("precision", c_i32),
       ("colsum", c_p), ("colsum_bs", c_i64),
       ("flags", c_i32),
+  ]
+
+
+class GemmDesc16(ctypes.Structure):
+  _fields_ = [
+      ("M", c_i32), ("N", c_i32), ("K", c_i32), ("dtype", c_i32),
+      ("A", c_p), ("a_ld", c_i64), ("a_mn", c_i32),
+      ("B", c_p), ("b_ld", c_i64), ("b_mn", c_i32),
+      ("C32", c_p), ("c32_ld", c_i64),
+      ("C16", c_p), ("c16_ld", c_i64), ("out16_scale", c_f),
+      ("bias", c_p),
+      ("add", c_p), ("add_ld", c_i64),
+      ("aux16", c_p), ("aux_ld", c_i64),
+      ("epilogue", c_i32), ("alpha", c_f),
+      ("p_drop", c_f), ("site", c_u32), ("seed", c_u64), ("seed_ctr", c_p),
+      ("batch", c_i32), ("batch_inner", c_i32),
+      ("a_bs0", c_i64), ("a_bs1", c_i64), ("b_bs0", c_i64), ("b_bs1", c_i64),
+      ("c_bs0", c_i64), ("c_bs1", c_i64), ("bias_bs", c_i64),
+      ("colsum", c_p), ("colsum_scale", c_f), ("colsum_bs", c_i64),
+      ("flags", c_i32),
+  ]
+
+
+class PackDesc(ctypes.Structure):
+  _fields_ = [
+      ("feats", c_p * MAX_EXPERTS), ("maxp", c_p * MAX_EXPERTS), ("out", c_p * MAX_EXPERTS),
+      ("in_", c_i32 * MAX_EXPERTS), ("ld", c_i32 * MAX_EXPERTS),
+      ("n", c_i32), ("B", c_i32), ("T", c_i32), ("dtype", c_i32),
   ]
 
 
@@ -70,6 +112,20 @@ SIGNATURES = {
     "mmt_sims_combine_bwd": (c_i32, [c_p] * 4 + [c_i32] * 5 + [c_p, c_p, c_p]),
     "mmt_max_margin_fwd_bwd": (c_i32, [c_p, c_i32, c_f, c_i32, c_p, c_p, c_p, c_p]),
     "mmt_adam_step": (c_i32, [c_p] * 4 + [c_i64] + [c_f] * 5 + [c_i32, c_f, c_p]),
+    # ---- 16-bit operand path ----
+    "mmt_gemm16": (c_i32, [ctypes.POINTER(GemmDesc16), c_p]),
+    "mmt_cast16": (c_i32, [c_p, c_i64, c_i32, c_i64, c_p, c_i32, c_i64, c_f, c_f, c_u64, c_p, c_u32, c_i32, c_p]),
+    "mmt_pack_inputs16": (c_i32, [ctypes.POINTER(PackDesc), c_p]),
+    "mmt_embed_ln16_fwd": (c_i32, [c_p] * 8 + [c_i32] * 5 + [c_f, c_f, c_u64, c_p, c_u32] + [c_p] * 8 + [c_i32, c_p]),
+    "mmt_embed_ln16_bwd": (c_i32, [c_p] * 10 + [c_i32] * 4 + [c_f, c_u64, c_p, c_u32, c_p, c_p, c_f] + [c_p] * 4 +
+                           [c_i32, c_p]),
+    "mmt_ln16_fwd": (c_i32, [c_p] * 3 + [c_i64, c_i32, c_f] + [c_p] * 4 + [c_i32, c_p]),
+    "mmt_ln16_bwd": (c_i32, [c_p] * 6 + [c_i64, c_i32, c_f, c_u64, c_p, c_u32, c_p, c_p, c_f] + [c_p] * 3 + [c_i32, c_p]),
+    "mmt_attention16_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_p, c_u32, c_p, c_p, c_i32,
+                                    c_p]),
+    "mmt_attention16_bwd": (c_i32, [c_p] * 5 + [c_i32] * 4 + [c_f, c_f, c_u64, c_p, c_u32, c_f] + [c_p] * 4 +
+                            [c_i32, c_p]),
+    "mmt_adam16_step": (c_i32, [c_p] * 5 + [c_i64] + [c_f] * 5 + [c_i32, c_p, c_f, c_i32, c_p]),
 }
 
 _lib = None
@@ -151,3 +207,36 @@ def gemm(M, N, K, A, a_ms, a_ks, B, b_ns, b_ks, C, c_ms, *, a_off=0, b_off=0, c_
   d.colsum = ptr(colsum, colsum_off)
   d.colsum_bs = colsum_bs
   check(load().mmt_gemm(ctypes.byref(d), stream_ptr()), "mmt_gemm")
+
+
+def gemm16(dt, M, N, K, A, a_ld, a_mn, B, b_ld, b_mn, *, a_off=0, b_off=0, C32=None, c32_off=0, c32_ld=0, C16=None,
+           c16_off=0, c16_ld=0, out16_scale=1.0, bias=None, bias_off=0, add=None, add_off=0, add_ld=0, aux16=None,
+           aux_off=0, aux_ld=0, epilogue=EPI_NONE, alpha=1.0, p_drop=0.0, seed=0, seed_ctr=None, site=0, batch=1,
+           batch_inner=1, a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), bias_bs=0, colsum=None, colsum_off=0,
+           colsum_scale=1.0, colsum_bs=0, split_k=False):
+  """C = epilogue(alpha * A B^T) on 16-bit operands (mmt_gemm16, include/mmt_b200.h).  Offsets in elements."""
+  d = GemmDesc16()
+  d.M, d.N, d.K, d.dtype = M, N, K, dt
+  d.A, d.a_ld, d.a_mn = ptr(A, a_off), a_ld, a_mn
+  d.B, d.b_ld, d.b_mn = ptr(B, b_off), b_ld, b_mn
+  d.C32, d.c32_ld = ptr(C32, c32_off), c32_ld
+  d.C16, d.c16_ld, d.out16_scale = ptr(C16, c16_off), c16_ld, out16_scale
+  d.bias = ptr(bias, bias_off)
+  d.add, d.add_ld = ptr(add, add_off), add_ld
+  d.aux16, d.aux_ld = ptr(aux16, aux_off), aux_ld
+  d.epilogue, d.alpha = epilogue, alpha
+  d.p_drop, d.site, d.seed, d.seed_ctr = p_drop, site, seed, seed_ctr
+  d.batch, d.batch_inner = batch, batch_inner
+  d.a_bs0, d.a_bs1 = a_bs
+  d.b_bs0, d.b_bs1 = b_bs
+  d.c_bs0, d.c_bs1 = c_bs
+  d.bias_bs = bias_bs
+  d.colsum, d.colsum_scale, d.colsum_bs = ptr(colsum, colsum_off), colsum_scale, colsum_bs
+  d.flags = GEMM_SPLIT_K if split_k else 0
+  check(load().mmt_gemm16(ctypes.byref(d), stream_ptr()), "mmt_gemm16")
+
+
+def cast16(dt, src, rows, cols, in_ld, out, out_cols, out_ld, scale=1.0, p_drop=0.0, seed=0, seed_ctr=None, site=0,
+           src_off=0, out_off=0):
+  check(load().mmt_cast16(ptr(src, src_off), rows, cols, in_ld, ptr(out, out_off), out_cols, out_ld, scale, p_drop,
+                          seed, seed_ctr, site, dt, stream_ptr()), "mmt_cast16")

@@ -1,0 +1,776 @@
+// Fused self-attention on 16-bit operands (model/bert.py:136-172 and its autograd), tcgen05 + TMA.
+// Nothing of size S x S ever reaches HBM: the forward keeps scores / probabilities in TMEM and saves only
+// the per-row log-sum-exp; the backward recomputes the probabilities from (Q, K, lse) and regenerates the
+// dropout decisions from (seed, site).
+//
+// FORWARD  one CTA per (b, h, 128-query tile), two CTAs per SM (88 KB smem, 256 TMEM columns each), so one
+//          CTA's loads and MMAs run under the other's softmax:
+//   warp 0    TMA: Q tile [128 x dh] and K block [224 x dh] (K-major, 128-byte swizzle); once the score MMAs
+//             have drained K, V [224 x dh] into the SAME buffer (the identical bytes are an MN-major B operand)
+//   warp 1    MMA: S = Q K^T (kind::f16, M=128, N=224, fp32 in TMEM), then O += P V with P read from TMEM
+//   warps 2-5 softmax, one thread per query row: scale + additive mask, max, exp2, row sum, dropout, P
+//             written IN PLACE over S as packed 16-bit pairs (unnormalised, in (0,1]); finally
+//             O * inv_keep / l -> ctx16, lse.  S > 224 takes several key blocks with the online-softmax
+//             rescale of the TMEM accumulator (then 512 TMEM columns, one CTA per SM).
+// BACKWARD one CTA per (b, h, 128-key tile), keys on the TMEM lanes; loop over 128-query tiles i:
+//   S^T = K_j Q_i^T and dPd^T = V_j dO_i^T                          (TMEM, 2 x 128 columns)
+//   8 softmax warps (two threads per key row): P^T = exp2(S^T*c + mask_k - lse_q), Pd^T = keep * P^T / (1-p),
+//   dS^T = P^T * (keep * dPd^T / (1-p) - delta_q) * scale  ->  Pd^T and dS^T as 16-bit tiles in shared memory
+//   (row = key, 128-byte swizzle: the same bytes serve as K-major A [keys x queries] and MN-major A [queries x keys])
+//   dV_j += Pd^T dO_i,  dK_j += dS^T Q_i  (TMEM accumulators across i),  dQ_i = dS K_j -> fp32 red.global.add
+//   into dq32 (each element receives one addend per key tile; two for S <= 256: order-independent).
+// delta_q = dO_q . O_q comes from a small pre-kernel; a post-kernel turns dq32 into the 16-bit dQ block of
+// dqkv16, takes its bias-gradient column sums and leaves dq32 zeroed for the next layer.
+//
+// Attention-probability dropout uses one 32-bit integer hash per PAIR of adjacent keys (16 random bits per
+// decision, P(drop) = floor(p * 65536) / 65536): with Philox the RNG alone was more than half of the softmax
+// instructions, and the softmax -- not the tensor core -- bounds this kernel at dh = 128.
+#include "cvt16.cuh"
+#include "rowvec.cuh"
+#include "tc_ptx.cuh"
+
+namespace mmt {
+namespace {
+using namespace tc;
+
+constexpr int DH = 128;
+constexpr float LOG2E = 1.44269504088896340736f;
+
+// ---- PTX helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t idesc16(int m, int n, bool a_mn, bool b_mn, bool bf16) {
+  const uint32_t f = bf16 ? 1u : 0u;
+  return (1u << 4) | (f << 7) | (f << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16u(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+        "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---- dropout decisions: one hash per pair of adjacent keys ------------------------------------------
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {       // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
+  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + site * 0x9E3779B9u + 0x6d6d7461u));
+}
+// random word of the key pair (key >> 1) of probability row `prow` (= (b*H + h)*S + q); low half -> even key
+__device__ __forceinline__ uint32_t drop_word(uint32_t key32, uint32_t prow, uint32_t half_pitch, uint32_t kpair) {
+  return hash32((prow * half_pitch + kpair) ^ key32);
+}
+
+struct AttArgs {
+  const float* mask;      // [B, S] 1 = attend
+  uint16_t* ctx16;        // [B*S, H*DH]
+  float* lse;             // [B, H, S]
+  int B, H, S;
+  float scale_log2;       // (1/sqrt(dh)) * log2(e)
+  float p_drop, inv_keep;
+  uint64_t seed;
+  const uint64_t* ctr;
+  uint32_t site;
+  int bf16;
+};
+
+// ======================================== forward ====================================================
+namespace fwd {
+constexpr int QM = 128, KB = 224;
+constexpr int THREADS = 192;                         // TMA warp, MMA warp, 4 softmax warps
+constexpr uint32_t Q_BYTES = QM * DH * 2;            // 32 KB: 2 sub-tiles [128 rows x 128 B]
+constexpr uint32_t QSUB = QM * 128;
+constexpr uint32_t KV_BYTES = KB * DH * 2;           // 56 KB: 2 sub-tiles [224 rows x 128 B]
+constexpr uint32_t KSUB = KB * 128;
+constexpr size_t SMEM = Q_BYTES + KV_BYTES + 1024 /*align*/ + 128 /*barriers*/ + KB * 4;
+
+__global__ void __launch_bounds__(THREADS, 2) attention16_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                     const __grid_constant__ CUtensorMap map_k,
+                                                                     const AttArgs args) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sq = smem;
+  uint8_t* skv = smem + Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + KV_BYTES);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* k_free = bars + 2;              // score MMAs have finished reading K
+  uint64_t* v_free = bars + 3;              // P V MMAs have finished reading V (and P)
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 5;              // 128 arrivals
+  uint64_t* o_full = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* smask = reinterpret_cast<float*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, S = args.S;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * QM;
+  const int nblk = (S + KB - 1) / KB;
+  const int d_model = H * DH;
+  const bool bf16 = args.bf16 != 0;
+  const uint32_t tm_cols = nblk == 1 ? 256u : 512u;   // single key block: O reuses the upper score columns
+  const uint32_t TM_S = 0, TM_O = nblk == 1 ? 128u : 256u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], i == 5 ? 128 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tm_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int row_q = b * S + q0;
+      for (int j = 0; j < nblk; ++j) {
+        const int row_k = b * S + j * KB;
+        mbar_wait(v_free, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(qk_full, (j == 0 ? Q_BYTES : 0) + KV_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j == 0) tma_load_2d(sq + t * QSUB, &map_q, qk_full, h * DH + 64 * t, row_q);
+          tma_load_2d(skv + t * KSUB, &map_k, qk_full, d_model + h * DH + 64 * t, row_k);
+        }
+        mbar_wait(k_free, j & 1);
+        mbar_arrive_expect_tx(v_full, KV_BYTES);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) tma_load_2d(skv + t * KSUB, &map_k, v_full, 2 * d_model + h * DH + 64 * t, row_k);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = idesc16(QM, KB, false, false, bf16);      // S[128 x 224] = Q K^T
+      const uint32_t idesc_o = idesc16(QM, DH, false, true, bf16);       // O[128 x dh] += P V (V MN-major)
+      for (int j = 0; j < nblk; ++j) {
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);            // P (aliasing S) no longer read
+        mbar_wait(qk_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint64_t da = make_smem_desc(smem_u32(sq) + (ks >> 2) * QSUB + (ks & 3) * 32, 16, 1024, 2);
+          const uint64_t db = make_smem_desc(smem_u32(skv) + (ks >> 2) * KSUB + (ks & 3) * 32, 16, 1024, 2);
+          umma_f16_ss(tmem + TM_S, da, db, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(k_free);
+        umma_commit(s_full);
+        mbar_wait(v_full, j & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < KB / 16; ++ks) {
+          // V as MN-major B: 64-wide dh chunks KSUB apart (LBO), 8-key atoms 1024 B apart (SBO), 16 keys = 2048 B
+          const uint64_t db = make_smem_desc(smem_u32(skv) + ks * 2048, KSUB, 1024, 2);
+          umma_f16_ts(tmem + TM_O, tmem + TM_S + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(v_free);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue (warps 2..5), thread = query row =====================
+    const int q = warp & 3;                                    // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;
+    const int qi = q0 + r;
+    const bool row_ok = qi < S;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float* mrow = args.mask + (int64_t)b * S;
+    const uint32_t prow = (uint32_t)(((int64_t)b * H + h) * S + qi);
+    const uint32_t half_pitch = (uint32_t)((S + 1) >> 1);
+    const uint64_t seed = args.seed + (args.ctr ? *args.ctr : 0);
+    const uint32_t key32 = drop_key(seed, args.site);
+    const uint32_t thr = (uint32_t)(args.p_drop * 65536.0f);
+    const bool drop = args.p_drop > 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * KB;
+      for (int t = threadIdx.x - 64; t < KB; t += 128) {
+        const int key = key0 + t;
+        smask[t] = key < S ? (1.0f - __ldg(mrow + key)) * (-10000.0f * LOG2E) : -INFINITY;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max of the masked, scaled scores (log2 domain)
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KB / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+#pragma unroll
+        for (int t = 0; t < 32; t += 4) {
+          const float4 mk = *reinterpret_cast<const float4*>(smask + c * 32 + t);
+          m_blk = fmaxf(fmaxf(m_blk, fmaf(v[t], args.scale_log2, mk.x)), fmaf(v[t + 1], args.scale_log2, mk.y));
+          m_blk = fmaxf(fmaxf(m_blk, fmaf(v[t + 2], args.scale_log2, mk.z)), fmaf(v[t + 3], args.scale_log2, mk.w));
+        }
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float alpha = (j == 0) ? 0.f : fast_ex2(m_run - m_new);
+      // pass 2: p = 2^(x - m), row sum of the un-dropped p, dropout, packed 16-bit P over S: columns 16c..16c+15
+      // receive the 32 probabilities of score columns 32c..32c+31, all of which this thread has already read
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < KB / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem + TM_S + lane_addr + c * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          const float2 mk = *reinterpret_cast<const float2*>(smask + c * 32 + t);
+          float p0 = fast_ex2(fmaf(v[t], args.scale_log2, mk.x) - m_new);
+          float p1 = fast_ex2(fmaf(v[t + 1], args.scale_log2, mk.y) - m_new);
+          l_blk += p0 + p1;
+          if (drop) {
+            const uint32_t w = drop_word(key32, prow, half_pitch, (uint32_t)((key0 + c * 32 + t) >> 1));
+            if ((w & 0xffffu) < thr) p0 = 0.f;
+            if ((w >> 16) < thr) p1 = 0.f;
+          }
+          pk[t >> 1] = pack2(p0, p1, bf16);
+        }
+        tmem_st16u(tmem + TM_S + lane_addr + c * 16, pk);
+      }
+      if (j > 0) {
+        // online softmax: rescale the running accumulator (previous P V has landed: o_full(j-1))
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < DH / 16; ++c) {
+          float v[16];
+          tmem_ld16f(tmem + TM_O + lane_addr + c * 16, v);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] *= alpha;
+          tmem_st16f(tmem + TM_O + lane_addr + c * 16, v);
+        }
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(p_full);
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // smask is rewritten by the next block
+    }
+    // epilogue: O * inv_keep / l -> ctx16, log-sum-exp for the backward pass
+    mbar_wait(o_full, (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv_l = args.inv_keep / l_run;
+    uint16_t* orow = args.ctx16 + ((int64_t)b * S + qi) * d_model + h * DH;
+#pragma unroll 1
+    for (int c = 0; c < DH / 16; ++c) {
+      float v[16];
+      tmem_ld16f(tmem + TM_O + lane_addr + c * 16, v);
+      if (row_ok) {
+        uint4 o0, o1;
+        o0.x = pack2(v[0] * inv_l, v[1] * inv_l, bf16);   o0.y = pack2(v[2] * inv_l, v[3] * inv_l, bf16);
+        o0.z = pack2(v[4] * inv_l, v[5] * inv_l, bf16);   o0.w = pack2(v[6] * inv_l, v[7] * inv_l, bf16);
+        o1.x = pack2(v[8] * inv_l, v[9] * inv_l, bf16);   o1.y = pack2(v[10] * inv_l, v[11] * inv_l, bf16);
+        o1.z = pack2(v[12] * inv_l, v[13] * inv_l, bf16); o1.w = pack2(v[14] * inv_l, v[15] * inv_l, bf16);
+        *reinterpret_cast<uint4*>(orow + c * 16) = o0;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+      }
+    }
+    if (row_ok && args.lse) args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_run)) * 0.69314718055994530942f;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, tm_cols);
+  }
+}
+}  // namespace fwd
+
+// ======================================== backward ===================================================
+struct AttBwdArgs {
+  const float* mask;      // [B, S]
+  const float* lse;       // [B, H, S] natural log
+  const float* delta;     // [B, H, S] dO . O in the scale16 domain
+  uint16_t* dqkv16;       // [B*S, 3*H*DH]; this kernel writes the K and V blocks
+  float* dq32;            // [B*S, H*DH] fp32, accumulated with red.add
+  float* dbias;           // [3*H*DH] fp32 bias gradient (K and V blocks accumulated here)
+  int B, H, S;
+  float scale, scale_log2;
+  float p_drop, inv_keep;
+  float inv_scale16;
+  uint64_t seed;
+  const uint64_t* ctr;
+  uint32_t site;
+  int bf16;
+};
+
+namespace bwd {
+constexpr int KT = 128, QT = 128;
+constexpr int THREADS = 320;                         // TMA warp, MMA warp, 8 softmax warps
+constexpr uint32_t TILE = 128 * DH * 2;              // 32 KB: 2 sub-tiles [128 rows x 128 B]
+constexpr uint32_t SUB = 128 * 128;                  // 16 KB
+constexpr size_t SMEM = 6 * TILE + 1024 /*align*/ + 128 /*barriers*/ + 2 * QT * 4;
+constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 384, TM_DQ = 0;
+
+__global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                                     const __grid_constant__ CUtensorMap map_do,
+                                                                     const AttBwdArgs args) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sk = smem;
+  uint8_t* sv = smem + TILE;
+  uint8_t* sq = smem + 2 * TILE;
+  uint8_t* sdo = smem + 3 * TILE;
+  uint8_t* sp = smem + 4 * TILE;                     // Pd^T  [keys x queries]
+  uint8_t* sds = smem + 5 * TILE;                    // dS^T  [keys x queries]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* st_full = bars + 2;              // S^T and dPd^T in TMEM
+  uint64_t* pds_full = bars + 3;             // Pd^T / dS^T tiles written (256 arrivals)
+  uint64_t* mma2_done = bars + 4;            // dV / dK / dQ MMAs of this query tile complete
+  uint64_t* dq_drained = bars + 5;           // dQ read out of TMEM (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_lse2 = reinterpret_cast<float*>(bars + 16);       // [QT] log2-domain lse of the query tile (+inf: no such query)
+  float* s_delta = s_lse2 + QT;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, S = args.S;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kt * KT;
+  const int nqt = (S + QT - 1) / QT;
+  const int d_model = H * DH;
+  const bool bf16 = args.bf16 != 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(st_full, 1);
+    mbar_init(pds_full, 256); mbar_init(mma2_done, 1); mbar_init(dq_drained, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int row_k = b * S + k0;
+      mbar_arrive_expect_tx(kv_full, 2 * TILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        tma_load_2d(sk + t * SUB, &map_qkv, kv_full, d_model + h * DH + 64 * t, row_k);
+        tma_load_2d(sv + t * SUB, &map_qkv, kv_full, 2 * d_model + h * DH + 64 * t, row_k);
+      }
+      for (int i = 0; i < nqt; ++i) {
+        if (i > 0) mbar_wait(mma2_done, (i - 1) & 1);          // Q_i / dO_i of the previous tile no longer read
+        const int row_q = b * S + i * QT;
+        mbar_arrive_expect_tx(qdo_full, 2 * TILE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_2d(sq + t * SUB, &map_qkv, qdo_full, h * DH + 64 * t, row_q);
+          tma_load_2d(sdo + t * SUB, &map_do, qdo_full, h * DH + 64 * t, row_q);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id_kk = idesc16(128, 128, false, false, bf16);   // A K-major, B K-major
+      const uint32_t id_km = idesc16(128, 128, false, true, bf16);    // A K-major, B MN-major
+      const uint32_t id_mm = idesc16(128, 128, true, true, bf16);     // A MN-major, B MN-major
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nqt; ++i) {
+        mbar_wait(qdo_full, i & 1);
+        if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);         // dQ_{i-1} has left the S^T columns
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {                  // S^T = K_j Q_i^T, dPd^T = V_j dO_i^T
+          const uint32_t off = (ks >> 2) * SUB + (ks & 3) * 32;
+          umma_f16_ss(tmem + TM_ST, make_smem_desc(smem_u32(sk) + off, 16, 1024, 2),
+                      make_smem_desc(smem_u32(sq) + off, 16, 1024, 2), id_kk, ks > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * SUB + (ks & 3) * 32;
+          umma_f16_ss(tmem + TM_DP, make_smem_desc(smem_u32(sv) + off, 16, 1024, 2),
+                      make_smem_desc(smem_u32(sdo) + off, 16, 1024, 2), id_kk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(st_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < QT / 16; ++ks) {                  // dV_j += Pd^T dO_i ; dK_j += dS^T Q_i  (k = queries)
+          const uint32_t aoff = (ks >> 2) * SUB + (ks & 3) * 32;
+          umma_f16_ss(tmem + TM_DV, make_smem_desc(smem_u32(sp) + aoff, 16, 1024, 2),
+                      make_smem_desc(smem_u32(sdo) + ks * 2048, SUB, 1024, 2), id_km, (i > 0 || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < QT / 16; ++ks) {
+          const uint32_t aoff = (ks >> 2) * SUB + (ks & 3) * 32;
+          umma_f16_ss(tmem + TM_DK, make_smem_desc(smem_u32(sds) + aoff, 16, 1024, 2),
+                      make_smem_desc(smem_u32(sq) + ks * 2048, SUB, 1024, 2), id_km, (i > 0 || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks)                    // dQ_i = dS K_j  (k = keys; both operands MN-major)
+          umma_f16_ss(tmem + TM_DQ, make_smem_desc(smem_u32(sds) + ks * 2048, SUB, 1024, 2),
+                      make_smem_desc(smem_u32(sk) + ks * 2048, SUB, 1024, 2), id_mm, ks > 0 ? 1u : 0u);
+        umma_commit(mma2_done);
+      }
+    }
+  } else {
+    // ===================== softmax backward + epilogues (warps 2..9) =====================
+    const int q4 = warp & 3;                                   // TMEM lane quarter
+    const int half = (warp - 2) >> 2;                          // which 64 of the 128 columns
+    const int r = q4 * 32 + lane;                              // key row within the tile == TMEM lane
+    const int key = k0 + r;
+    const bool key_ok = key < S;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const float mterm = key_ok ? (1.0f - __ldg(args.mask + (int64_t)b * S + key)) * (-10000.0f * LOG2E) : -INFINITY;
+    const uint64_t seed = args.seed + (args.ctr ? *args.ctr : 0);
+    const uint32_t key32 = drop_key(seed, args.site);
+    const uint32_t thr = (uint32_t)(args.p_drop * 65536.0f);
+    const bool drop = args.p_drop > 0.f;
+    const uint32_t half_pitch = (uint32_t)((S + 1) >> 1);
+    const uint32_t kpair = (uint32_t)key >> 1;
+    const uint32_t kshift = (key & 1) ? 16u : 0u;
+    const uint32_t prow0 = (uint32_t)(((int64_t)b * H + h) * S);
+    // this thread's 128-byte row (64 queries) of the Pd^T / dS^T tiles: sub-tile `half`, row r, 16-byte chunk c at c ^ (r & 7)
+    const uint32_t row_base = (uint32_t)half * SUB + (uint32_t)r * 128;
+    const uint32_t sp_u = smem_u32(sp), sds_u = smem_u32(sds);
+    for (int i = 0; i < nqt; ++i) {
+      const int qbase = i * QT;
+      // per-query vectors of this tile (the previous tile's readers are past pds_full of i-1 ... and its dQ drain)
+      for (int t = threadIdx.x - 64; t < QT; t += 256) {
+        const int qq = qbase + t;
+        const bool ok = qq < S;
+        s_lse2[t] = ok ? __ldg(args.lse + ((int64_t)b * H + h) * S + qq) * LOG2E : INFINITY;
+        s_delta[t] = ok ? __ldg(args.delta + ((int64_t)b * H + h) * S + qq) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(st_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {                             // 16 query columns at a time
+        const int col = half * 64 + c * 16;
+        float sv_[16], dp[16];
+        {
+          uint32_t r0[16], r1[16];
+          tmem_ld16u(tmem + TM_ST + lane_addr + col, r0);
+          tmem_ld16u(tmem + TM_DP + lane_addr + col, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) { sv_[t] = __uint_as_float(r0[t]); dp[t] = __uint_as_float(r1[t]); }
+        }
+        uint32_t pp[8], dd[8];
+#pragma unroll
+        for (int t = 0; t < 16; t += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int qc = col + t + u;
+            const float p = fast_ex2(fmaf(sv_[t + u], args.scale_log2, mterm) - s_lse2[qc]);
+            float keep = args.inv_keep;
+            if (drop) {
+              const uint32_t w = drop_word(key32, prow0 + (uint32_t)(qbase + qc), half_pitch, kpair);
+              if (((w >> kshift) & 0xffffu) < thr) keep = 0.f;
+            }
+            pv[u] = p * keep;
+            dv[u] = p * fmaf(dp[t + u], keep, -s_delta[qc]) * args.scale;
+          }
+          pp[t >> 1] = pack2(pv[0], pv[1], bf16);
+          dd[t >> 1] = pack2(dv[0], dv[1], bf16);
+        }
+        const uint32_t ch0 = (uint32_t)(c * 2), sw = (uint32_t)(r & 7);
+        sts128u(sp_u + row_base + (((ch0) ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
+        sts128u(sp_u + row_base + (((ch0 + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
+        sts128u(sds_u + row_base + (((ch0) ^ sw) << 4), dd[0], dd[1], dd[2], dd[3]);
+        sts128u(sds_u + row_base + (((ch0 + 1) ^ sw) << 4), dd[4], dd[5], dd[6], dd[7]);
+      }
+      fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // dQ_i out of TMEM: lane = query row, this thread's 64 of the dh columns
+      mbar_wait(mma2_done, i & 1);
+      tc_fence_after();
+      {
+        const int qq = qbase + r;
+        float* drow = args.dq32 + ((int64_t)b * S + qq) * d_model + h * DH + half * 64;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[16];
+          tmem_ld16f(tmem + TM_DQ + lane_addr + half * 64 + c * 16, v);
+          if (qq < S) {
+#pragma unroll
+            for (int t = 0; t < 16; t += 4)
+              atomicAdd(reinterpret_cast<float4*>(drow + c * 16 + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+    }
+    // epilogue: dV_j, dK_j (lane = key row) -> dqkv16 V and K blocks; bias-gradient column sums
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tm = which == 0 ? TM_DV : TM_DK;
+      const int blk = which == 0 ? 2 : 1;                       // column block of dqkv16: Q | K | V
+      uint16_t* orow = args.dqkv16 + ((int64_t)b * S + key) * (3 * d_model) + blk * d_model + h * DH + half * 64;
+      float* bsum = args.dbias + blk * d_model + h * DH + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tmem_ld16f(tmem + tm + lane_addr + half * 64 + c * 16, v);
+        if (key_ok) {
+          uint4 o0, o1;
+          o0.x = pack2(v[0], v[1], bf16);   o0.y = pack2(v[2], v[3], bf16);
+          o0.z = pack2(v[4], v[5], bf16);   o0.w = pack2(v[6], v[7], bf16);
+          o1.x = pack2(v[8], v[9], bf16);   o1.y = pack2(v[10], v[11], bf16);
+          o1.z = pack2(v[12], v[13], bf16); o1.w = pack2(v[14], v[15], bf16);
+          *reinterpret_cast<uint4*>(orow + c * 16) = o0;
+          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float sum = warp_sum(key_ok ? v[t] : 0.f);
+          if (lane == t) v[0] = sum;                            // lane t keeps column t's sum (in v[0])
+        }
+        if (lane < 16) atomicAdd(bsum + c * 16 + lane, v[0] * args.inv_scale16);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// delta[b,h,q] = sum_c dO[b,q,h*dh+c] * O[b,q,h*dh+c]   (one warp per token row, dh = 128: 4 elements per lane and head)
+__global__ void __launch_bounds__(256) attn_delta16_kernel(const uint16_t* __restrict__ dctx16, const uint16_t* __restrict__ ctx16,
+                                                           int64_t rows, int S, int H, float* __restrict__ delta, int bf16) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int d_model = H * DH;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    const int64_t b = r / S, q = r % S;
+    for (int h = 0; h < H; ++h) {
+      const float4 a = unpack4(*reinterpret_cast<const uint2*>(dctx16 + r * d_model + h * DH + lane * 4), bf16 != 0);
+      const float4 o = unpack4(*reinterpret_cast<const uint2*>(ctx16 + r * d_model + h * DH + lane * 4), bf16 != 0);
+      const float s = warp_sum((a.x * o.x + a.y * o.y) + (a.z * o.z + a.w * o.w));
+      if (lane == 0) delta[(b * H + h) * S + q] = s;
+    }
+  }
+}
+
+// dq32 [rows, d] -> the Q block of dqkv16 (16-bit, already in the scale16 domain), its bias-gradient column sums
+// (divided by scale16), and dq32 zeroed again for the next layer's accumulation.
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) attn_dq_finish_kernel(float* __restrict__ dq32, int64_t rows,
+                                                                    uint16_t* __restrict__ dqkv16, float* __restrict__ dbias,
+                                                                    float inv_scale16, int bf16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int d = 128 * VEC;
+  __shared__ float4 red[WARPS * VEC * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[VEC], zero[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
+    float4 g[VEC];
+    load_row<VEC>(dq32 + r * d, lane, g);
+    store_row<VEC>(dq32 + r * d, lane, zero);
+    store_row16<VEC>(dqkv16 + r * 3 * d, lane, g, 1.0f, bf16 != 0);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i].x += g[i].x; acc[i].y += g[i].y; acc[i].z += g[i].z; acc[i].w += g[i].w; }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) F4_OP(acc[i], acc[i].x * inv_scale16, acc[i].y * inv_scale16, acc[i].z * inv_scale16, acc[i].w * inv_scale16);
+  flush_cols<VEC>(acc, dbias, lane, warp, red);
+}
+}  // namespace bwd
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D 16-bit tensor map [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128-byte swizzle
+int make_map16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int dtype,
+                  const char* what) {
+  static EncodeTiledFn enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return (EncodeTiledFn) nullptr;
+  }();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 2) % 16 == 0, MMT_E_ALIGN,
+                "tensor map %s needs a 16-byte aligned base and row pitch", what);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == MMT_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
+int set_smem_once(const void* kern, size_t bytes, bool* flag, const char* what) {
+  if (*flag) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return cuda_status(e, what);
+  *flag = true;
+  return 0;
+}
+
+}  // namespace
+}  // namespace mmt
+
+using namespace mmt;
+
+extern "C" int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t B, int32_t H, int32_t S, int32_t dh,
+                                   float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
+                                   void* ctx16, float* lse, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(qkv16 && mask && ctx16, MMT_E_ARG, "mmt_attention16_fwd: null pointer");
+  MMT_ARG_CHECK(dh == DH, MMT_E_SHAPE, "mmt_attention16_fwd: head dim %d unsupported (only %d)", dh, DH);
+  MMT_ARG_CHECK(B > 0 && H > 0 && S > 0 && B <= 65535 && H <= 65535, MMT_E_SHAPE, "mmt_attention16_fwd: bad shape B=%d H=%d S=%d", B, H, S);
+  MMT_ARG_CHECK((int64_t)B * H * S * ((S + 1) / 2) < (1ll << 32), MMT_E_SHAPE, "mmt_attention16_fwd: dropout counter overflow");
+  MMT_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f, MMT_E_ARG, "mmt_attention16_fwd: p_drop=%f", (double)p_drop);
+  MMT_ARG_CHECK(dtype == MMT_DT_F16 || dtype == MMT_DT_BF16, MMT_E_ARG, "mmt_attention16_fwd: bad dtype %d", dtype);
+  const int64_t rows = (int64_t)B * S, cols = 3LL * H * DH;
+  CUtensorMap mq, mk;
+  int rc = make_map16_2d(&mq, qkv16, rows, cols, cols, fwd::QM, dtype, "Q");
+  if (rc) return rc;
+  rc = make_map16_2d(&mk, qkv16, rows, cols, cols, fwd::KB, dtype, "K/V");
+  if (rc) return rc;
+  AttArgs a;
+  a.mask = mask; a.ctx16 = reinterpret_cast<uint16_t*>(ctx16); a.lse = lse;
+  a.B = B; a.H = H; a.S = S;
+  a.scale_log2 = scale * LOG2E;
+  a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = dtype == MMT_DT_BF16 ? 1 : 0;
+  static bool configured = false;
+  rc = set_smem_once((const void*)fwd::attention16_fwd_kernel, fwd::SMEM, &configured, "attention16_fwd smem attribute");
+  if (rc) return rc;
+  dim3 grid((S + fwd::QM - 1) / fwd::QM, H, B);
+  launch_pdl(fwd::attention16_fwd_kernel, grid, dim3(fwd::THREADS), fwd::SMEM, (cudaStream_t)stream, mq, mk, a);
+  MMT_LAUNCH_CHECK("attention16_fwd_kernel");
+  return 0;
+}
+
+extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const void* dctx16, const float* lse,
+                                   const float* mask, int32_t B, int32_t H, int32_t S, int32_t dh, float scale,
+                                   float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float scale16,
+                                   void* dqkv16, float* dq32, float* delta, float* dbias, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(qkv16 && ctx16 && dctx16 && lse && mask && dqkv16 && dq32 && delta && dbias, MMT_E_ARG,
+                "mmt_attention16_bwd: null pointer");
+  MMT_ARG_CHECK(dh == DH, MMT_E_SHAPE, "mmt_attention16_bwd: head dim %d unsupported (only %d)", dh, DH);
+  MMT_ARG_CHECK(B > 0 && H > 0 && S > 0 && B <= 65535 && H <= 65535, MMT_E_SHAPE, "mmt_attention16_bwd: bad shape B=%d H=%d S=%d", B, H, S);
+  MMT_ARG_CHECK((int64_t)B * H * S * ((S + 1) / 2) < (1ll << 32), MMT_E_SHAPE, "mmt_attention16_bwd: dropout counter overflow");
+  MMT_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f && scale16 > 0.f, MMT_E_ARG, "mmt_attention16_bwd: p_drop=%f scale16=%f", (double)p_drop, (double)scale16);
+  MMT_ARG_CHECK(dtype == MMT_DT_F16 || dtype == MMT_DT_BF16, MMT_E_ARG, "mmt_attention16_bwd: bad dtype %d", dtype);
+  const int d_model = H * DH;
+  CHECK_D(d_model);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)B * S;
+  const int bf16 = dtype == MMT_DT_BF16 ? 1 : 0;
+  {
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    launch_pdl(bwd::attn_delta16_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<const uint16_t*>(dctx16),
+               reinterpret_cast<const uint16_t*>(ctx16), rows, S, H, delta, bf16);
+    MMT_LAUNCH_CHECK("attn_delta16_kernel");
+  }
+  CUtensorMap mqkv, mdo;
+  int rc = make_map16_2d(&mqkv, qkv16, rows, 3LL * d_model, 3LL * d_model, 128, dtype, "QKV");
+  if (rc) return rc;
+  rc = make_map16_2d(&mdo, dctx16, rows, d_model, d_model, 128, dtype, "dO");
+  if (rc) return rc;
+  AttBwdArgs a;
+  a.mask = mask; a.lse = lse; a.delta = delta;
+  a.dqkv16 = reinterpret_cast<uint16_t*>(dqkv16); a.dq32 = dq32; a.dbias = dbias;
+  a.B = B; a.H = H; a.S = S;
+  a.scale = scale; a.scale_log2 = scale * LOG2E;
+  a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  a.inv_scale16 = 1.0f / scale16;
+  a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = bf16;
+  static bool configured = false;
+  rc = set_smem_once((const void*)bwd::attention16_bwd_kernel, bwd::SMEM, &configured, "attention16_bwd smem attribute");
+  if (rc) return rc;
+  dim3 grid((S + bwd::KT - 1) / bwd::KT, H, B);
+  launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);
+  MMT_LAUNCH_CHECK("attention16_bwd_kernel");
+  {
+    int grid2 = row_grid(rows);
+    if (grid2 > num_sms() * 2) grid2 = num_sms() * 2;
+    DISPATCH_VEC(d_model, (launch_pdl(bwd::attn_dq_finish_kernel<V>, dim3(grid2), dim3(WARPS * 32), 0, st, dq32, rows,
+                                      reinterpret_cast<uint16_t*>(dqkv16), dbias, 1.0f / scale16, bf16)));
+    MMT_LAUNCH_CHECK("attn_dq_finish_kernel");
+  }
+  return 0;
+}

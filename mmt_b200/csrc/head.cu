@@ -1,6 +1,7 @@
 // Retrieval head: text GatedEmbeddingUnit tail (BatchNorm + context gating + L2 norm), text
 // mixture weights, weighted similarity combine, bi-directional max-margin loss, fused Adam.
 // All HBM/latency-bound: coalesced float4 traffic, warp-shuffle reductions.
+#include "cvt16.cuh"
 #include "rowvec.cuh"
 
 namespace mmt {
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n4, int64_t n, float lr, float b1, float b2,
                                                    float eps, float wd, int step, const uint64_t* __restrict__ ctr,
-                                                   float gscale) {
+                                                   float gscale, uint16_t* __restrict__ p16, int bf16) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_bc[2];
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       P[q] -= (lr / bc1) * (Mm[q] / denom);
     }
     reinterpret_cast<float4*>(p)[i] = pp;
+    if (p16 != nullptr) reinterpret_cast<uint2*>(p16)[i] = pack4(pp, bf16 != 0);     // the GEMMs' 16-bit weight copy
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
@@ -543,6 +545,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       m[i] = b1 * m[i] + (1.f - b1) * gr;
       v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
       p[i] -= (lr / bc1) * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
+      if (p16 != nullptr) p16[i] = pack1(p[i], bf16 != 0);
     }
   }
 }
@@ -733,8 +736,26 @@ int mmt_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (blocks < 1) blocks = 1;
-  launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale);
+  launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n4, n, lr, beta1, beta2, eps, weight_decay, step, g_step_ctr, grad_scale, (uint16_t*)nullptr, 0);
   MMT_LAUNCH_CHECK("adam");
+  return 0;
+}
+
+int mmt_adam16_step(float* p, const float* g, float* m, float* v, void* p16, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, const uint64_t* step_ctr,
+                    float grad_scale, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(p && g && m && v, MMT_E_ARG, "mmt_adam16_step: null pointer");
+  MMT_ARG_CHECK(step >= 1 || step_ctr != nullptr, MMT_E_ARG, "mmt_adam16_step: step=%d must be >= 1", step);
+  MMT_ARG_CHECK(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                ((uintptr_t)v % 16 == 0) && ((uintptr_t)p16 % 8 == 0), MMT_E_ALIGN, "mmt_adam16_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  if (blocks < 1) blocks = 1;
+  launch_pdl(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n4, n, lr, beta1, beta2,
+             eps, weight_decay, step, step_ctr, grad_scale, reinterpret_cast<uint16_t*>(p16), dtype == MMT_DT_BF16 ? 1 : 0);
+  MMT_LAUNCH_CHECK("adam16");
   return 0;
 }
 

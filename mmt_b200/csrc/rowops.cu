@@ -6,6 +6,7 @@
 // row reductions are warp shuffles.  Column reductions (dgamma/dbeta/dbias) are kept in
 // registers across a grid-stride loop over rows, reduced across the block's warps through shared
 // memory and flushed with one vector atomic per lane per block.
+#include "cvt16.cuh"
 #include "rowvec.cuh"
 
 namespace mmt {
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
     const float* __restrict__ beta, int B, int M, int T, int max_pos, float eps, float p_drop,
     uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ h, float* __restrict__ mask,
     int32_t* __restrict__ pos_ids, int32_t* __restrict__ type_ids, float* __restrict__ inv_norm,
-    float* __restrict__ mean_o, float* __restrict__ rstd_o) {
+    float* __restrict__ mean_o, float* __restrict__ rstd_o, void* __restrict__ h16, int bf16) {
   pdl_trigger();
   pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
       }
     }
     store_row<VEC>(h + r * d, lane, e);
+    if (h16 != nullptr) store_row16<VEC>(reinterpret_cast<uint16_t*>(h16) + r * d, lane, e, 1.0f, bf16 != 0);
     if (lane == 0) {
       mask[r] = mk; pos_ids[r] = pos; type_ids[r] = type; inv_norm[r] = invn;
       mean_o[r] = mean; rstd_o[r] = rstd;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
     const float* __restrict__ type_emb, const float* __restrict__ gamma, int B, int M, int T,
     float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr, float* __restrict__ dproj,
     float* __restrict__ dpos_emb, float* __restrict__ dtype_emb, float* __restrict__ dgamma,
-    float* __restrict__ dbeta) {
+    float* __restrict__ dbeta, void* __restrict__ dproj16, float scale16, int bf16) {
   pdl_trigger();
   pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
       for (int i = 0; i < VEC; ++i) F4_OP(de[i], de[i].x * invn, de[i].y * invn, de[i].z * invn, de[i].w * invn);
     }
     store_row<VEC>(dproj + prow * d, lane, de);
+    if (dproj16 != nullptr) store_row16<VEC>(reinterpret_cast<uint16_t*>(dproj16) + prow * d, lane, de, scale16, bf16 != 0);
   }
   flush_cols<VEC>(ag, dgamma, lane, warp, red);
   flush_cols<VEC>(ab, dbeta, lane, warp, red);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
     const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr,
     float* __restrict__ dz, float* __restrict__ dt, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, float* __restrict__ dbias) {
+    float* __restrict__ dbeta, float* __restrict__ dbias, void* __restrict__ dt16, float scale16, int bf16) {
   pdl_trigger();
   pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
@@ -270,8 +273,9 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
         float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
         F4_OP(gy[i], gy[i].x * sc.x, gy[i].y * sc.y, gy[i].z * sc.z, gy[i].w * sc.w);
       }
-      store_row<VEC>(dt + r * d, lane, gy);
+      if (dt != nullptr) store_row<VEC>(dt + r * d, lane, gy);
     }
+    if (dt16 != nullptr) store_row16<VEC>(reinterpret_cast<uint16_t*>(dt16) + r * d, lane, gy, scale16, bf16 != 0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       abias[i].x += gy[i].x; abias[i].y += gy[i].y; abias[i].z += gy[i].z; abias[i].w += gy[i].w;
@@ -536,6 +540,104 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 16-bit operand path: plain LayerNorm of the GEMM-epilogue output, operand casts, input packing
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(WARPS * 32) ln16_fwd_kernel(
+    const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
+    float eps, float* __restrict__ y, void* __restrict__ y16, float* __restrict__ mean_o, float* __restrict__ rstd_o,
+    int bf16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int d = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  float4 g[VEC], bt[VEC];
+  load_row<VEC>(gamma, lane, g);
+  load_row<VEC>(beta, lane, bt);
+  for (int64_t r = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * WARPS) {
+    float4 x[VEC];
+    load_row<VEC>(z + r * d, lane, x);
+    float mean, rstd;
+    ln_stats<VEC>(x, d, eps, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      F4_OP(x[i], (x[i].x - mean) * rstd * g[i].x + bt[i].x, (x[i].y - mean) * rstd * g[i].y + bt[i].y,
+            (x[i].z - mean) * rstd * g[i].z + bt[i].z, (x[i].w - mean) * rstd * g[i].w + bt[i].w);
+    if (y != nullptr) store_row<VEC>(y + r * d, lane, x);
+    if (y16 != nullptr) store_row16<VEC>(reinterpret_cast<uint16_t*>(y16) + r * d, lane, x, 1.0f, bf16 != 0);
+    if (lane == 0) { mean_o[r] = mean; rstd_o[r] = rstd; }
+  }
+}
+
+// out[r, c4*4 .. +3] = rn16(mask * in * scale); columns >= cols are written as zero up to out_cols
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ in, int64_t rows, int cols, int64_t in_ld,
+                                                     uint16_t* __restrict__ out, int out_cols, int64_t out_ld, float scale,
+                                                     float p_drop, uint64_t seed, const uint64_t* __restrict__ ctr,
+                                                     uint32_t site, int bf16, int vec) {
+  pdl_trigger();
+  pdl_wait();
+  if (ctr != nullptr) seed += *ctr;
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const int n4 = (out_cols + 3) >> 2;
+  const int64_t total = rows * n4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n4;
+    const int c = (int)(i % n4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = in + r * in_ld + c;
+    if (vec && c + 4 <= cols) v = *reinterpret_cast<const float4*>(p);
+    else {
+      if (c < cols) v.x = p[0];
+      if (c + 1 < cols) v.y = p[1];
+      if (c + 2 < cols) v.z = p[2];
+      if (c + 3 < cols) v.w = p[3];
+    }
+    if (p_drop > 0.f) {
+      const float4 sc = dropout_scale4(seed, site, (uint32_t)r, (uint32_t)(c >> 2), p_drop, inv_keep);
+      F4_OP(v, v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
+    }
+    F4_OP(v, v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    uint16_t* q = out + r * out_ld + c;
+    if (vec && c + 4 <= out_cols) *reinterpret_cast<uint2*>(q) = pack4(v, bf16 != 0);
+    else {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      for (int t = 0; t < 4; ++t) if (c + t < out_cols) q[t] = pack1(vv[t], bf16 != 0);
+    }
+  }
+}
+
+// blockIdx.y = expert; rows (b, j) of [B, T+1]: j == 0 -> maxp[b], else feats[b, j-1]
+__global__ void __launch_bounds__(256) pack_inputs16_kernel(const mmt_pack_desc pd) {
+  pdl_trigger();
+  pdl_wait();
+  const int k = blockIdx.y;
+  const int in = pd.in[k], ld = pd.ld[k], T = pd.T;
+  const bool bf16 = pd.dtype == MMT_DT_BF16;
+  const float* __restrict__ feats = pd.feats[k];
+  const float* __restrict__ maxp = pd.maxp[k];
+  uint16_t* __restrict__ out = reinterpret_cast<uint16_t*>(pd.out[k]);
+  const int n4 = ld >> 2;                                  // ld % 8 == 0
+  const int64_t total = (int64_t)pd.B * (T + 1) * n4;
+  const bool vec = (in & 3) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n4;
+    const int c = (int)(i % n4) * 4;
+    const int b = (int)(r / (T + 1)), j = (int)(r % (T + 1));
+    const float* p = (j == 0 ? maxp + (int64_t)b * in : feats + ((int64_t)b * T + (j - 1)) * in) + c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && c + 4 <= in) v = *reinterpret_cast<const float4*>(p);
+    else {
+      if (c < in) v.x = p[0];
+      if (c + 1 < in) v.y = p[1];
+      if (c + 2 < in) v.z = p[2];
+      if (c + 3 < in) v.w = p[3];
+    }
+    *reinterpret_cast<uint2*>(out + r * ld + c) = pack4(v, bf16);
+  }
+}
+
 }  // namespace
 }  // namespace mmt
 
@@ -556,7 +658,7 @@ int mmt_embed_ln_fwd(const float* proj, const float* ft, const float* ind, const
   const int64_t rows = (int64_t)B * (1 + M * (T + 1));
   DISPATCH_VEC(d, (launch_pdl(embed_ln_fwd_kernel<V>, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       proj, ft, ind, type_idx, pos_emb, type_emb, gamma, beta, B, M, T, max_pos, eps, p_drop, seed,
-      site, g_step_ctr, h, mask, pos_ids, type_ids, inv_norm, mean, rstd)));
+      site, g_step_ctr, h, mask, pos_ids, type_ids, inv_norm, mean, rstd, (void*)nullptr, 0)));
   MMT_LAUNCH_CHECK("embed_ln_fwd");
   return 0;
 }
@@ -575,7 +677,7 @@ int mmt_embed_ln_bwd(const float* dh, const float* proj, const int32_t* pos_ids,
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   DISPATCH_VEC(d, (launch_pdl(embed_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
       dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, M, T, p_drop,
-      seed, site, g_step_ctr, dproj, dpos_emb, dtype_emb, dgamma, dbeta)));
+      seed, site, g_step_ctr, dproj, dpos_emb, dtype_emb, dgamma, dbeta, (void*)nullptr, 1.0f, 0)));
   MMT_LAUNCH_CHECK("embed_ln_bwd");
   return 0;
 }
@@ -603,7 +705,8 @@ int mmt_res_ln_bwd(const float* dy, const float* dy2, const float* z, const floa
   int grid = row_grid(rows);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
   DISPATCH_VEC(d, (launch_pdl(res_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, 
-      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, g_step_ctr, dz, dt, dgamma, dbeta, dbias)));
+      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, g_step_ctr, dz, dt, dgamma, dbeta, dbias,
+      (void*)nullptr, 1.0f, 0)));
   MMT_LAUNCH_CHECK("res_ln_bwd");
   return 0;
 }
@@ -700,6 +803,112 @@ int mmt_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
   launch_pdl(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(in),
              reinterpret_cast<uint2*>(out_bf16), n / 4);
   MMT_LAUNCH_CHECK("cast_bf16");
+  return 0;
+}
+
+int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, int32_t out_cols,
+               int64_t out_ld, float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
+               int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(in && out, MMT_E_ARG, "mmt_cast16: null pointer");
+  MMT_ARG_CHECK(rows >= 0 && cols >= 0 && out_cols >= cols && in_ld >= cols && out_ld >= out_cols, MMT_E_SHAPE,
+                "mmt_cast16: bad shape rows=%lld cols=%d out_cols=%d", (long long)rows, cols, out_cols);
+  MMT_ARG_CHECK(dtype == MMT_DT_F16 || dtype == MMT_DT_BF16, MMT_E_ARG, "mmt_cast16: bad dtype %d", dtype);
+  CHECK_P(p_drop);
+  const int64_t total = rows * ((out_cols + 3) / 4);
+  if (total == 0) return 0;
+  const int vec = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && (in_ld % 4 == 0) && (out_ld % 4 == 0);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  launch_pdl(cast16_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, in, rows, cols, in_ld,
+             reinterpret_cast<uint16_t*>(out), out_cols, out_ld, scale, p_drop, seed, seed_ctr, site,
+             dtype == MMT_DT_BF16 ? 1 : 0, vec);
+  MMT_LAUNCH_CHECK("cast16");
+  return 0;
+}
+
+int mmt_pack_inputs16(const mmt_pack_desc* d, void* stream) {
+  MMT_ARG_CHECK(d != nullptr, MMT_E_ARG, "mmt_pack_inputs16: null descriptor");
+  MMT_ARG_CHECK(d->n >= 1 && d->n <= MMT_MAX_EXPERTS && d->B > 0 && d->T > 0, MMT_E_SHAPE,
+                "mmt_pack_inputs16: n=%d B=%d T=%d", d->n, d->B, d->T);
+  int max_ld = 0;
+  for (int k = 0; k < d->n; ++k) {
+    MMT_ARG_CHECK(d->feats[k] && d->maxp[k] && d->out[k], MMT_E_ARG, "mmt_pack_inputs16: null pointer (expert %d)", k);
+    MMT_ARG_CHECK(d->ld[k] >= d->in[k] && d->ld[k] % 8 == 0 && ((uintptr_t)d->out[k] % 16) == 0, MMT_E_ALIGN,
+                  "mmt_pack_inputs16: expert %d pitch %d (in %d) must be a multiple of 8", k, d->ld[k], d->in[k]);
+    MMT_ARG_CHECK(((uintptr_t)d->feats[k] % 16) == 0 && ((uintptr_t)d->maxp[k] % 16) == 0, MMT_E_ALIGN,
+                  "mmt_pack_inputs16: expert %d inputs must be 16-byte aligned", k);
+    if (d->ld[k] > max_ld) max_ld = d->ld[k];
+  }
+  const int64_t total = (int64_t)d->B * (d->T + 1) * (max_ld / 4);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16 / d->n + 1;
+  if (blocks > cap) blocks = cap;
+  launch_pdl(pack_inputs16_kernel, dim3((int)blocks, d->n), dim3(256), 0, (cudaStream_t)stream, *d);
+  MMT_LAUNCH_CHECK("pack_inputs16");
+  return 0;
+}
+
+int mmt_embed_ln16_fwd(const float* proj, const float* ft, const float* ind, const int32_t* type_idx,
+                       const float* pos_emb, const float* type_emb, const float* gamma, const float* beta,
+                       int32_t B, int32_t M, int32_t T, int32_t d, int32_t max_pos, float eps, float p_drop,
+                       uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* h, void* h16, float* mask,
+                       int32_t* pos_ids, int32_t* type_ids, float* inv_norm, float* mean, float* rstd,
+                       int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(proj && ft && ind && type_idx && pos_emb && type_emb && gamma && beta && h && h16 && mask &&
+                pos_ids && type_ids && inv_norm && mean && rstd, MMT_E_ARG, "mmt_embed_ln16_fwd: null pointer");
+  MMT_ARG_CHECK(B > 0 && M > 0 && T > 0 && max_pos > 0, MMT_E_SHAPE, "mmt_embed_ln16_fwd: bad shape B=%d M=%d T=%d", B, M, T);
+  CHECK_D(d); CHECK_P(p_drop);
+  const int64_t rows = (int64_t)B * (1 + M * (T + 1));
+  DISPATCH_VEC(d, (launch_pdl(embed_ln_fwd_kernel<V>, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream,
+      proj, ft, ind, type_idx, pos_emb, type_emb, gamma, beta, B, M, T, max_pos, eps, p_drop, seed,
+      site, seed_ctr, h, mask, pos_ids, type_ids, inv_norm, mean, rstd, h16, dtype == MMT_DT_BF16 ? 1 : 0)));
+  MMT_LAUNCH_CHECK("embed_ln16_fwd");
+  return 0;
+}
+
+int mmt_embed_ln16_bwd(const float* dh, const float* proj, const int32_t* pos_ids, const int32_t* type_ids,
+                       const float* inv_norm, const float* mean, const float* rstd, const float* pos_emb,
+                       const float* type_emb, const float* gamma, int32_t B, int32_t M, int32_t T, int32_t d,
+                       float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* dproj,
+                       void* dproj16, float scale16, float* dpos_emb, float* dtype_emb, float* dgamma,
+                       float* dbeta, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(dh && proj && pos_ids && type_ids && inv_norm && mean && rstd && pos_emb && type_emb &&
+                gamma && dproj && dproj16 && dpos_emb && dtype_emb && dgamma && dbeta, MMT_E_ARG, "mmt_embed_ln16_bwd: null pointer");
+  CHECK_D(d); CHECK_P(p_drop);
+  const int64_t rows = (int64_t)B * (1 + M * (T + 1));
+  int grid = row_grid(rows);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  DISPATCH_VEC(d, (launch_pdl(embed_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream,
+      dh, proj, pos_ids, type_ids, inv_norm, mean, rstd, pos_emb, type_emb, gamma, B, M, T, p_drop,
+      seed, site, seed_ctr, dproj, dpos_emb, dtype_emb, dgamma, dbeta, dproj16, scale16, dtype == MMT_DT_BF16 ? 1 : 0)));
+  MMT_LAUNCH_CHECK("embed_ln16_bwd");
+  return 0;
+}
+
+int mmt_ln16_fwd(const float* z, const float* gamma, const float* beta, int64_t rows, int32_t d, float eps,
+                 float* y, void* y16, float* mean, float* rstd, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(z && gamma && beta && (y || y16) && mean && rstd, MMT_E_ARG, "mmt_ln16_fwd: null pointer");
+  CHECK_D(d);
+  if (rows == 0) return 0;
+  DISPATCH_VEC(d, (launch_pdl(ln16_fwd_kernel<V>, dim3(row_grid(rows)), dim3(WARPS * 32), 0, (cudaStream_t)stream,
+      z, gamma, beta, rows, eps, y, y16, mean, rstd, dtype == MMT_DT_BF16 ? 1 : 0)));
+  MMT_LAUNCH_CHECK("ln16_fwd");
+  return 0;
+}
+
+int mmt_ln16_bwd(const float* dy, const float* dy2, const float* z, const float* mean, const float* rstd,
+                 const float* gamma, int64_t rows, int32_t d, float p_drop, uint64_t seed,
+                 const uint64_t* seed_ctr, uint32_t site, float* dz, void* dt16, float scale16, float* dgamma,
+                 float* dbeta, float* dbias, int32_t dtype, void* stream) {
+  MMT_ARG_CHECK(dy && z && mean && rstd && gamma && dz && dt16 && dgamma && dbeta, MMT_E_ARG, "mmt_ln16_bwd: null pointer");
+  CHECK_D(d); CHECK_P(p_drop);
+  if (rows == 0) return 0;
+  int grid = row_grid(rows);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  DISPATCH_VEC(d, (launch_pdl(res_ln_bwd_kernel<V>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream,
+      dy, dy2, z, mean, rstd, gamma, rows, p_drop, seed, site, seed_ctr, dz, (float*)nullptr, dgamma, dbeta, dbias,
+      dt16, scale16, dtype == MMT_DT_BF16 ? 1 : 0)));
+  MMT_LAUNCH_CHECK("ln16_bwd");
   return 0;
 }
 

@@ -42,14 +42,28 @@ class Config:
     # PREC_TF32 (default): every linear layer and the attention matmuls run on the tcgen05
     # tensor-core kernels (tf32 operands, fp32 accumulate; outputs within 1e-3 of the fp32
     # reference, tests/test_gpu_parity.py).  PREC_FP32: CUDA-core fp32 FMAs everywhere (~1e-6).
-    self.precision = PREC_TF32
-    self.attn_precision = None          # attention matmuls; None -> same as `precision`
+    #   PREC_F16 (default) / PREC_BF16: the 16-bit operand path of engine16.py -- producers emit round-to-nearest
+    #   fp16 (tf32's 10-bit mantissa at half the bytes) or bf16 (BASELINE config 5) operand copies, fp32
+    #   accumulation / statistics / residuals / gradients, fused attention forward AND backward.
+    self.precision = _lib.PREC_F16
+    self.attn_precision = None          # attention matmuls (fp32 / tf32 modes); None -> same as `precision`
+    self.w16 = None                     # engine16.Weights16 (16-bit weight copies), owned by the module
+    self.seed_ctr = None                # device pointer of a uint64 step counter added to every dropout seed
+    self.scale16_override = None
     # flash-style fused attention forward (scores / probabilities never leave TMEM); the backward
     # pass recomputes the probabilities.  Needs the tf32 attention path and dh == 128.
     self.fused_attention = True
     # training: the fused forward also streams P / dropout(P) out for the backward pass (S <= 224);
     # False = keep nothing of size S x S and recompute Q K^T + softmax in the backward instead
     self.save_attention_probs = os.environ.get("MMT_SAVE_PROBS", "1") != "0"
+
+
+  @property
+  def scale16(self):
+    """Power-of-two factor carried by 16-bit gradient tensors (fp16 range); 1 for bf16."""
+    if self.scale16_override is not None:
+      return float(self.scale16_override)
+    return 65536.0 if self.precision == _lib.PREC_F16 else 1.0
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -91,6 +105,9 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   ft/ind: [M, B, T] features_t / features_ind
   Returns (vid [B,M,d] L2-normalised expert embeddings, Saved).
   """
+  if _lib.is16(cfg.precision):
+    from . import engine16
+    return engine16.video_forward(cfg, flat, feats, maxp, ft, ind, training, seed)
   L = cfg.layout
   d, ff, H, dh, M = cfg.d, cfg.ff, cfg.H, cfg.dh, cfg.M
   B, T = feats[0].shape[0], feats[0].shape[1]
@@ -234,6 +251,9 @@ def head_forward(cfg, flat, bufs, text, training, seed):
   text : [R, text_dim]  (txt_bert CLS features, R = B*caps)        model.py:371-379
   Returns (txt [R,M,d], tw [R,M], Saved).
   """
+  if _lib.is16(cfg.precision):
+    from . import engine16
+    return engine16.head_forward(cfg, flat, bufs, text, training, seed)
   L = cfg.layout
   d, M = cfg.d, cfg.M
   R = text.shape[0]
@@ -290,6 +310,9 @@ def zero_small_grads(cfg, gflat):
 def head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext=True):
   """Backward of head_forward: text-head parameter gradients into `gflat`; returns
   d loss / d text [R, text_dim] (or None)."""
+  if _lib.is16(cfg.precision):
+    from . import engine16
+    return engine16.head_backward(cfg, flat, gflat, sv, dtxt, dtw, need_dtext)
   L = cfg.layout
   d, M = cfg.d, cfg.M
   R = sv.R
@@ -356,6 +379,9 @@ def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
   accumulated -- zero it first with zero_small_grads -- big matrices overwritten).
   `on_layer_done(l)` is called once layer l's weight-matrix gradients have been enqueued (the
   data-parallel path starts their all-reduce there)."""
+  if _lib.is16(cfg.precision):
+    from . import engine16
+    return engine16.video_backward(cfg, flat, gflat, sv, dvid, on_layer_done)
   L = cfg.layout
   d, ff, H, dh, M = cfg.d, cfg.ff, cfg.H, cfg.dh, cfg.M
   B, T, S, Sp = sv.B, sv.T, sv.S, sv.Sp
@@ -510,7 +536,7 @@ def sims_forward(vid, txt, vw, tw, caps, merge_avg):
   return sims, dots
 
 
-def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg, precision=PREC_FP32):
+def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg, precision=PREC_FP32, scale16=1.0):
   """Backward of sims_forward.  `precision` applies to the two gradient products only (the forward dot
   products always stay fp32 FMAs: ranking at the similarity boundary must be exact)."""
   lib = _lib.load()
@@ -522,6 +548,10 @@ def sims_backward(dsims, dots, vid, txt, vw, tw, caps, merge_avg, precision=PREC
                                  1 if (merge_avg and caps > 1) else 0, ptr(ddots), ptr(dtw),
                                  stream_ptr()), "mmt_sims_combine_bwd")
   # dtxt[:, m, :] = ddots_m @ vid_m ; dvid[:, m, :] = ddots_m^T @ txt_m
+  if _lib.is16(precision):
+    from . import engine16
+    dvid, dtxt = engine16.sims_backward_products(_lib.dt_of(precision), ddots, vid, txt, scale16)
+    return dvid, dtxt, dtw
   dtxt = torch.empty_like(txt)
   dvid = torch.empty_like(vid)
   tc = precision == PREC_TF32 and Nv % 4 == 0 and Nq % 4 == 0          # TMA strides: 16-byte multiples

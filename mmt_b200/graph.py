@@ -27,7 +27,7 @@ class GraphedTrainStep:
     self.kw, self.text = kwargs, text
     dev = net.flat.device
     self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
-    _lib.check(_lib.load().mmt_set_step_counter(_lib.ptr(self.ctr)), "mmt_set_step_counter")
+    self._attach()
     set_text(self.text)
 
     def one_step():
@@ -51,6 +51,31 @@ class GraphedTrainStep:
       self.loss = one_step()
     # the python-side step counters advanced once during capture; replays advance the device one
 
+  def _attach(self):
+    """Point the step's kernels at the device counter: the 16-bit path takes it per call (net.cfg.seed_ctr,
+    opt.step_ctr); the fp32 / tf32 entry points read the library-wide pointer."""
+    if _lib.is16(self.net.cfg.precision):
+      self.net.cfg.seed_ctr = _lib.ptr(self.ctr)
+      if hasattr(self.opt, "step_ctr"):
+        self.opt.step_ctr = _lib.ptr(self.ctr)
+    else:
+      _lib.check(_lib.load().mmt_set_step_counter(_lib.ptr(self.ctr)), "mmt_set_step_counter")
+
+  def _detach(self):
+    if _lib.is16(self.net.cfg.precision):
+      self.net.cfg.seed_ctr = None
+      if hasattr(self.opt, "step_ctr"):
+        self.opt.step_ctr = None
+    else:
+      _lib.check(_lib.load().mmt_set_step_counter(None), "mmt_set_step_counter")
+
+  def __del__(self):
+    try:
+      if getattr(self, "ctr", None) is not None:
+        self._detach()
+    except Exception:
+      pass
+
   def load(self, kwargs, text):
     """Refresh the static inputs from other (host-pinned or device) tensors."""
     for k, v in kwargs.items():
@@ -70,7 +95,8 @@ class GraphedTrainStep:
     step counts so Adam's bias correction continues where the replays left off."""
     torch.cuda.synchronize()
     n = int(self.ctr.item())
-    _lib.check(_lib.load().mmt_set_step_counter(None), "mmt_set_step_counter")
+    self._detach()
+    self.ctr = None
     if hasattr(self.opt, "t"):
       self.opt.t += n
     self.net._step += n

@@ -70,19 +70,19 @@ class EncodeFn(torch.autograd.Function):
 class SimsFn(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, vid, txt, vw, tw, caps, merge_avg, bwd_precision=engine.PREC_FP32):
+  def forward(ctx, vid, txt, vw, tw, caps, merge_avg, bwd_precision=engine.PREC_FP32, scale16=1.0):
     vid, txt, vw, tw = vid.contiguous(), txt.contiguous(), vw.contiguous(), tw.contiguous()
     sims, dots = engine.sims_forward(vid, txt, vw, tw, caps, merge_avg)
     ctx.save_for_backward(vid, txt, vw, tw, dots)
-    ctx.caps, ctx.merge_avg, ctx.bwd_precision = caps, merge_avg, bwd_precision
+    ctx.caps, ctx.merge_avg, ctx.bwd_precision, ctx.scale16 = caps, merge_avg, bwd_precision, scale16
     return sims
 
   @staticmethod
   def backward(ctx, dsims):
     vid, txt, vw, tw, dots = ctx.saved_tensors
     dvid, dtxt, dtw = engine.sims_backward(dsims.contiguous(), dots, vid, txt, vw, tw, ctx.caps,
-                                           ctx.merge_avg, ctx.bwd_precision)
-    return dvid, dtxt, None, dtw, None, None, None
+                                           ctx.merge_avg, ctx.bwd_precision, ctx.scale16)
+    return dvid, dtxt, None, dtw, None, None, None, None
 
 
 def sharded_cross_view_inner_product(vid_embds, text_embds, vid_weights, text_weights, subspaces,
@@ -281,7 +281,24 @@ class CENet(nn.Module):
     object.__setattr__(self, "flat", flat)
     object.__setattr__(self, "buf_flat", buf)
     self._gflat = None
+    self.cfg.w16 = None
     self.cfg.type_idx_dev = torch.tensor(self.cfg.type_idx, dtype=torch.int32, device=dev)
+
+  def _prepare16(self):
+    """16-bit operand modes: make sure the 16-bit weight copy exists and is current.  FusedAdam refreshes
+    it inside its kernel; after any other change of the parameters (another optimizer, load_state_dict,
+    .to()) torch has bumped the flat buffer's version counter and one cast pass runs here."""
+    cfg = self.cfg
+    if not _lib.is16(cfg.precision):
+      return
+    from ..engine16 import Weights16
+    w = cfg.w16
+    if w is None or w.flat16.device != self.flat.device or w.dt != _lib.dt_of(cfg.precision):
+      w = cfg.w16 = Weights16(cfg, self.flat)
+    sig = 0
+    for p in self._hot_params():
+      sig += p._version
+    w.refresh(cfg, self.flat, sig)
 
   def enable_data_parallel(self, group=None):
     """Shard the train step by batch over the ranks of `group` (mmt_b200/parallel.py): in
@@ -355,6 +372,7 @@ class CENet(nn.Module):
     ft = torch.stack([prep(features_t[m]) for m in mods], 0)
     ind = torch.stack([prep(features_ind[m]) for m in mods], 0)
 
+    self._prepare16()
     self._step += 1
     seed = (torch.initial_seed() * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
     anchor = next((p for p in self._hot_params() if p.requires_grad), None)
@@ -375,7 +393,7 @@ class CENet(nn.Module):
     merge = "avg" if self.training else self.test_caption_mode
     self.merge_caption_similarities = merge
     if out == "conf":
-      conf = SimsFn.apply(vid, txt, vid_weights, tw, caps, merge == "avg", self.cfg.precision)
+      conf = SimsFn.apply(vid, txt, vid_weights, tw, caps, merge == "avg", self.cfg.precision, self.cfg.scale16)
       return {"modalities": mods, "cross_view_conf_matrix": conf}
     return {
         "vid_embds": vid,                                             # [b, M, d]

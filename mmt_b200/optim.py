@@ -1,10 +1,17 @@
 """Fused Adam over the model's flat parameter / gradient buffers (one kernel per contiguous run).
 
 Semantics = torch.optim.Adam (reference train.py:95-98: Adam(lr, weight_decay) over
-filter(requires_grad, model.parameters())): parameters that received no gradient (the unused
-pooler, frozen parameters) are skipped, exactly as torch skips `p.grad is None`.
-Parameters outside the flat buffer (e.g. the third-party text encoder) are handed to a regular
-torch.optim.Adam.
+filter(requires_grad, model.parameters())): parameters that received no gradient in this step (the unused
+pooler, frozen parameters, anything when no backward ran) are skipped, exactly as torch skips `p.grad is None`.
+Parameters outside the flat buffer (e.g. the third-party text encoder) are handed to a regular torch.optim.Adam.
+
+The object quacks like a torch optimizer where the reference's trainer touches one: `param_groups` (the
+learning rate is read from `param_groups[0]["lr"]` at every step, so `torch.optim.lr_scheduler.StepLR` and
+`pytorch_warmup` dampening -- train.py:101-108, trainer.py:245-246 -- drive it), `zero_grad`, `step`,
+`state_dict` / `load_state_dict` (moments and step count, base_trainer.py:367, 442).
+
+In the 16-bit operand modes the same kernel also writes the GEMMs' 16-bit weight copy, so no separate cast
+pass runs in a FusedAdam-driven step.
 """
 import torch
 
@@ -15,7 +22,6 @@ class FusedAdam:
 
   def __init__(self, net, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
     self.net = net
-    self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
     self.grad_scale = grad_scale
     self.t = 0
     self.m = torch.zeros_like(net.flat)
@@ -24,7 +30,20 @@ class FusedAdam:
     others = [p for p in net.parameters() if id(p) not in hot and p.requires_grad]
     self.other = torch.optim.Adam(others, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay) \
         if others else None
+    self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+    group = dict(self.defaults, params=[p for p in net._hot_params() if p.requires_grad], initial_lr=lr)
+    self.param_groups = [group] + (self.other.param_groups if self.other is not None else [])
     self._runs = None
+    self.step_ctr = None        # device uint64 pointer added to the bias-correction step (CUDA-graph replays)
+
+  # hyper-parameters are read from param_groups[0] at every step (lr schedulers mutate it)
+  @property
+  def lr(self):
+    return self.param_groups[0]["lr"]
+
+  @lr.setter
+  def lr(self, v):
+    self.param_groups[0]["lr"] = v
 
   def _compute_runs(self):
     """Contiguous [offset, end) ranges of the flat buffer whose parameters are trained."""
@@ -49,31 +68,72 @@ class FusedAdam:
     if self.other is not None:
       self.other.zero_grad(set_to_none=set_to_none)
 
+  def state_dict(self):
+    return {"t": self.t, "m": self.m, "v": self.v, "param_groups": [{k: v for k, v in g.items() if k != "params"}
+                                                                   for g in self.param_groups[:1]],
+            "other": self.other.state_dict() if self.other is not None else None}
+
+  def load_state_dict(self, sd):
+    self.t = int(sd["t"])
+    self.m.copy_(sd["m"])
+    self.v.copy_(sd["v"])
+    for k, v in sd["param_groups"][0].items():
+      self.param_groups[0][k] = v
+    if self.other is not None and sd.get("other") is not None:
+      self.other.load_state_dict(sd["other"])
+
   def step(self):
     net = self.net
     if self.m.device != net.flat.device:
       self.m, self.v = self.m.to(net.flat.device), self.v.to(net.flat.device)
     if self._runs is None:
       self._runs = self._compute_runs()
+    params = net._hot_params()
     g = net._grad_flat()
     # gradients are normally views of net._gflat (EncodeFn publishes them without copies); if the
     # caller accumulated / replaced them, gather them back into the flat layout first
     views = net.__dict__.get("_grad_views")
-    for i, p in enumerate(net._hot_params()):
+    fresh = False
+    missing = []
+    for i, p in enumerate(params):
       if p.grad is None:
+        if p.requires_grad and not net._names[i].startswith("vid_bert.pooler."):
+          missing.append(i)
         continue
+      fresh = True
       if views is not None and views[0] == g.data_ptr() and p.grad is views[1][i]:
         continue                                            # the common case: already a view of g
       v = net.layout.view(g, net._names[i])
       if p.grad.data_ptr() != v.data_ptr():
         v.copy_(p.grad)
-    self.t += 1
-    lib = _lib.load()
-    st = _lib.stream_ptr()
-    for lo, hi in self._runs:
-      _lib.check(lib.mmt_adam_step(_lib.ptr(net.flat, lo), _lib.ptr(g, lo), _lib.ptr(self.m, lo),
-                                   _lib.ptr(self.v, lo), hi - lo, self.lr, self.betas[0],
-                                   self.betas[1], self.eps, self.wd, self.t, self.grad_scale, st),
-                 "mmt_adam_step")
+    if fresh:
+      self.t += 1
+      g_hp = self.param_groups[0]
+      lr, (b1, b2), eps, wd = g_hp["lr"], g_hp["betas"], g_hp["eps"], g_hp["weight_decay"]
+      if missing:
+        # torch.optim.Adam skips parameters without a gradient: run only over the others (rare path)
+        runs = []
+        skip = set(missing)
+        for i, p in enumerate(params):
+          if p.grad is None or i in skip:
+            continue
+          seg = net.layout.segments[net._names[i]]
+          runs.append([seg.offset, min(seg.offset + (seg.numel + 3) // 4 * 4, net.layout.numel)])
+      else:
+        runs = self._runs
+      lib = _lib.load()
+      st = _lib.stream_ptr()
+      w16 = net.cfg.w16 if _lib.is16(net.cfg.precision) else None
+      for lo, hi in runs:
+        if w16 is not None:
+          _lib.check(lib.mmt_adam16_step(_lib.ptr(net.flat, lo), _lib.ptr(g, lo), _lib.ptr(self.m, lo),
+                                         _lib.ptr(self.v, lo), _lib.ptr(w16.flat16, lo), hi - lo, lr, b1, b2, eps, wd,
+                                         self.t, self.step_ctr, self.grad_scale, w16.dt, st), "mmt_adam16_step")
+        else:
+          _lib.check(lib.mmt_adam_step(_lib.ptr(net.flat, lo), _lib.ptr(g, lo), _lib.ptr(self.m, lo),
+                                       _lib.ptr(self.v, lo), hi - lo, lr, b1, b2, eps, wd, self.t,
+                                       self.grad_scale, st), "mmt_adam_step")
+      if w16 is not None:
+        w16.refresh_padded(net.cfg, net.flat)      # row-padded ReduceDim copies (two small casts)
     if self.other is not None:
       self.other.step()

@@ -54,8 +54,45 @@ def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda", precision="fp32
                                "attention_probs_dropout_prob": dropout},
               txt_bert=TxtStub(hidden.to(device)))
   net.load_state_dict(P, strict=True)
-  net.cfg.precision = _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
+  net.cfg.precision = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16,
+                       "bf16": _lib.PREC_BF16}[precision]
   return net.to(device)
+
+
+def grad_errors(net, ref_grads):
+  """Gradient parity of a CUDA net against oracle gradients {name: tensor}.
+  Returns (whole-gradient max-norm relative error, whole-gradient rel-L2, worst per-tensor (name, err) with the
+  per-tensor scale max(|g_ref|_max, 1e-2 * global max), worst per-tensor rel-L2 (name, err))."""
+  gmax = max(float(g.abs().max()) for g in ref_grads.values())
+  num = den = 0.0
+  emax = 0.0
+  worst, worst_l2 = ("", 0.0), ("", 0.0)
+  for name, g in ref_grads.items():
+    got = net._param(name).grad
+    assert got is not None, name
+    diff = got.detach().cpu().double() - g.double()
+    emax = max(emax, float(diff.abs().max()))
+    num += float((diff * diff).sum())
+    den += float((g.double() * g.double()).sum())
+    e = float(diff.abs().max()) / max(float(g.abs().max()), 1e-2 * gmax)
+    if e > worst[1]:
+      worst = (name, e)
+    l2 = float(diff.norm()) / max(float(g.double().norm()), 1e-30)
+    if l2 > worst_l2[1] and float(g.abs().max()) > 1e-2 * gmax:
+      worst_l2 = (name, l2)
+  return emax / gmax, (num / den) ** 0.5, worst, worst_l2
+
+
+def oracle_step(P, batch, cfg):
+  """Oracle forward + MaxMarginRankingLoss + backward (dropout off): conf, loss, {name: grad}."""
+  Pr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+        for k, v in P.items()}
+  ref = O.cenet_forward(Pr, batch, cfg, training=True, out="conf", text_feat=batch["text_feat"])
+  conf = ref["cross_view_conf_matrix"]
+  loss = O.max_margin_ranking_loss(conf, 0.05, True)
+  loss.backward()
+  grads = {k: v.grad for k, v in Pr.items() if getattr(v, "grad", None) is not None}
+  return conf.detach(), float(loss.detach()), grads
 
 
 def batch_kwargs(batch, device=None):

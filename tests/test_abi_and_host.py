@@ -8,7 +8,7 @@ import re
 import pytest
 import torch
 
-from mmt_b200 import _lib, engine
+from mmt_b200 import _lib, engine, engine16
 from oracle import mmt_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -108,6 +108,38 @@ class _Recorder:
         assert self.inside(d.bias + 4 * (z * d.bias_bs + N - 1), 4)
     return 0
 
+  def mmt_gemm16(self, dref, stream):
+    d = dref._obj
+    self.calls.append("mmt_gemm16")
+    M, N, K = d.M, d.N, d.K
+    assert d.a_ld % 8 == 0 and d.b_ld % 8 == 0 and d.A % 16 == 0 and d.B % 16 == 0, "TMA alignment"
+    assert d.C32 or d.C16
+    for z in range(d.batch):
+      z0, z1 = z // d.batch_inner, z % d.batch_inner
+      a = d.A + 2 * (z0 * d.a_bs0 + z1 * d.a_bs1)
+      b = d.B + 2 * (z0 * d.b_bs0 + z1 * d.b_bs1)
+      zc = z0 * d.c_bs0 + z1 * d.c_bs1
+      for (m, k) in ((0, 0), (M - 1, K - 1), (M - 1, 0), (0, K - 1)):
+        off = k * d.a_ld + m if d.a_mn else m * d.a_ld + k
+        assert self.inside(a + 2 * off, 2), ("A", M, N, K, m, k)
+      for (n, k) in ((0, 0), (N - 1, K - 1), (N - 1, 0), (0, K - 1)):
+        off = k * d.b_ld + n if d.b_mn else n * d.b_ld + k
+        assert self.inside(b + 2 * off, 2), ("B", M, N, K, n, k)
+      for (m, n) in ((0, 0), (M - 1, N - 1)):
+        if d.C32:
+          assert self.inside(d.C32 + 4 * (zc + m * d.c32_ld + n), 4), ("C32", M, N, K)
+        if d.C16:
+          assert self.inside(d.C16 + 2 * (zc + m * d.c16_ld + n), 2), ("C16", M, N, K)
+        if d.add:
+          assert self.inside(d.add + 4 * (zc + m * d.add_ld + n), 4)
+        if d.aux16:
+          assert self.inside(d.aux16 + 2 * (zc + m * d.aux_ld + n), 2)
+      if d.bias:
+        assert self.inside(d.bias + 4 * (z * d.bias_bs + N - 1), 4)
+      if d.colsum:
+        assert self.inside(d.colsum + 4 * (z1 * d.colsum_bs + N - 1), 4)
+    return 0
+
   def __getattr__(self, name):
     if not name.startswith("mmt_"):
       raise AttributeError(name)
@@ -135,6 +167,8 @@ def recorder(monkeypatch):
   monkeypatch.setattr(engine, "ptr", ptr)
   monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
   monkeypatch.setattr(engine, "stream_ptr", lambda: 0)
+  monkeypatch.setattr(engine16, "ptr", ptr)
+  monkeypatch.setattr(engine16, "stream_ptr", lambda: 0)
   return rec
 
 
@@ -161,8 +195,41 @@ def _mini_net():
   return net, ed
 
 
+def test_engine16_dry_run_addresses_only_owned_memory(recorder):
+  """The 16-bit operand sequencing (engine16.py): every pointer / extent handed to the library lies inside a
+  tensor the host code allocated, TMA alignment rules hold for every GEMM operand."""
+  net, ed = _mini_net()
+  net.cfg.precision = _lib.PREC_F16
+  net._prepare16()
+  B, T = 5, 7
+  batch = O.synth_batch(ed, B, T, text_dim=96)
+  mods = list(ed.keys())
+  feats = [batch["features"][m] for m in mods]
+  maxp = [batch["features_maxpool"][m] for m in mods]
+  ft = torch.stack([batch["features_t"][m] for m in mods], 0)
+  ind = torch.stack([batch["features_ind"][m] for m in mods], 0)
+  for training in (True, False):
+    vid, txt, tw, sv = engine.encode_forward(net.cfg, net.flat, net.buf_flat, batch["text_feat"],
+                                             feats, maxp, ft, ind, training, 123)
+    assert vid.shape == (B, 3, 128) and txt.shape == (B, 3, 128) and tw.shape == (B, 3)
+    g = torch.zeros_like(net.flat)
+    dtext = engine.encode_backward(net.cfg, net.flat, g, sv, torch.zeros_like(vid),
+                                   torch.zeros_like(txt), torch.zeros_like(tw))
+    assert dtext.shape == (B, 96)
+  sims, dots = engine.sims_forward(vid, txt, torch.ones(B, 3) / 3, tw, 1, True)
+  engine.sims_backward(torch.zeros_like(sims), dots, vid, txt, torch.ones(B, 3) / 3, tw, 1, True,
+                       precision=_lib.PREC_F16, scale16=net.cfg.scale16)
+  assert recorder.calls.count("mmt_gemm16") > 60
+  for name in ("mmt_pack_inputs16", "mmt_embed_ln16_fwd", "mmt_embed_ln16_bwd", "mmt_ln16_fwd", "mmt_ln16_bwd",
+               "mmt_attention16_fwd", "mmt_attention16_bwd", "mmt_cast16", "mmt_readout_norm_fwd",
+               "mmt_readout_norm_bwd", "mmt_geu_gate_fwd", "mmt_geu_gate_bwd", "mmt_moe_softmax_fwd",
+               "mmt_moe_softmax_bwd", "mmt_sims_combine_fwd", "mmt_sims_combine_bwd", "mmt_colsum"):
+    assert name in recorder.calls, name
+
+
 def test_engine_dry_run_addresses_only_owned_memory(recorder):
   net, ed = _mini_net()
+  net.cfg.precision = _lib.PREC_TF32
   B, T = 5, 7
   batch = O.synth_batch(ed, B, T, text_dim=96)
   mods = list(ed.keys())
