@@ -303,8 +303,11 @@ int mmt_gemm16(const mmt_gemm16_desc* d, void* stream);
 
 /* out[r, c] = rn16(mask * in[r*in_ld + c] * scale) for c < cols, 0 for cols <= c < out_cols (row pitch out_ld
  * elements).  p_drop > 0 applies the (seed, site, r, c/4) dropout mask of mmt_dropout (moe_txt_dropout,
- * model/model.py:274).  The per-step weight copy (rows = 1) and every small fp32 -> 16-bit operand copy. */
-int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, int32_t out_cols,
+ * model/model.py:274).  The per-step weight copy (rows = 1) and every small fp32 -> 16-bit operand copy.
+ * out_lo (may be NULL; same shape as out): the second term of a two-term split, x*scale ~= out + out_lo / 2048,
+ * for the few small products that need more than one 11-bit significand (the similarity's gradient products,
+ * the root of every video / text gradient): A B = Ah Bh + (Ah Bl + Al Bh) / 2048 to ~2^-21. */
+int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, void* out_lo, int32_t out_cols,
                int64_t out_ld, float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
                int32_t dtype, void* stream);
 

@@ -114,7 +114,7 @@ SIGNATURES = {
     "mmt_adam_step": (c_i32, [c_p] * 4 + [c_i64] + [c_f] * 5 + [c_i32, c_f, c_p]),
     # ---- 16-bit operand path ----
     "mmt_gemm16": (c_i32, [ctypes.POINTER(GemmDesc16), c_p]),
-    "mmt_cast16": (c_i32, [c_p, c_i64, c_i32, c_i64, c_p, c_i32, c_i64, c_f, c_f, c_u64, c_p, c_u32, c_i32, c_p]),
+    "mmt_cast16": (c_i32, [c_p, c_i64, c_i32, c_i64, c_p, c_p, c_i32, c_i64, c_f, c_f, c_u64, c_p, c_u32, c_i32, c_p]),
     "mmt_pack_inputs16": (c_i32, [ctypes.POINTER(PackDesc), c_p]),
     "mmt_embed_ln16_fwd": (c_i32, [c_p] * 8 + [c_i32] * 5 + [c_f, c_f, c_u64, c_p, c_u32] + [c_p] * 8 + [c_i32, c_p]),
     "mmt_embed_ln16_bwd": (c_i32, [c_p] * 10 + [c_i32] * 4 + [c_f, c_u64, c_p, c_u32, c_p, c_p, c_f] + [c_p] * 4 +
@@ -237,6 +237,6 @@ def gemm16(dt, M, N, K, A, a_ld, a_mn, B, b_ld, b_mn, *, a_off=0, b_off=0, C32=N
 
 
 def cast16(dt, src, rows, cols, in_ld, out, out_cols, out_ld, scale=1.0, p_drop=0.0, seed=0, seed_ctr=None, site=0,
-           src_off=0, out_off=0):
-  check(load().mmt_cast16(ptr(src, src_off), rows, cols, in_ld, ptr(out, out_off), out_cols, out_ld, scale, p_drop,
-                          seed, seed_ctr, site, dt, stream_ptr()), "mmt_cast16")
+           src_off=0, out_off=0, out_lo=None):
+  check(load().mmt_cast16(ptr(src, src_off), rows, cols, in_ld, ptr(out, out_off), ptr(out_lo), out_cols, out_ld, scale,
+                          p_drop, seed, seed_ctr, site, dt, stream_ptr()), "mmt_cast16")

@@ -102,13 +102,6 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
 }
 
 // ---- dropout decisions: one hash per pair of adjacent keys ------------------------------------------
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {       // "lowbias32" integer finaliser
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
-  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + site * 0x9E3779B9u + 0x6d6d7461u));
-}
 // random word of the key pair (key >> 1) of probability row `prow` (= (b*H + h)*S + q); low half -> even key
 __device__ __forceinline__ uint32_t drop_word(uint32_t key32, uint32_t prow, uint32_t half_pitch, uint32_t kpair) {
   return hash32((prow * half_pitch + kpair) ^ key32);
@@ -494,8 +487,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
     const uint32_t kpair = (uint32_t)key >> 1;
     const uint32_t kshift = (key & 1) ? 16u : 0u;
     const uint32_t prow0 = (uint32_t)(((int64_t)b * H + h) * S);
-    // this thread's 128-byte row (64 queries) of the Pd^T / dS^T tiles: sub-tile `half`, row r, 16-byte chunk c at c ^ (r & 7)
-    const uint32_t row_base = (uint32_t)half * SUB + (uint32_t)r * 128;
+    // Pd^T / dS^T tiles: sub-tile = 64 queries, row = key, 16-byte chunk c of a row stored at c ^ (row & 7)
     const uint32_t sp_u = smem_u32(sp), sds_u = smem_u32(sds);
     for (int i = 0; i < nqt; ++i) {
       const int qbase = i * QT;
@@ -509,9 +501,20 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(st_full, i & 1);
       tc_fence_after();
+      // 16 query columns at a time; the two column halves take alternate 16-column chunks so that a ragged last
+      // query tile (S = 218: 90 of 128 columns) leaves both with the same amount of work
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {                             // 16 query columns at a time
-        const int col = half * 64 + c * 16;
+      for (int cc = half; cc < 8; cc += 2) {
+        const int col = cc * 16;
+        const uint32_t rb = (uint32_t)(cc >> 2) * SUB + (uint32_t)r * 128;      // sub-tile (64 queries), this key's row
+        const uint32_t ch0 = (uint32_t)((cc & 3) * 2), sw = (uint32_t)(r & 7);
+        if (qbase + col >= S || k0 + q4 * 32 >= S) {            // no such queries / no such keys in this warp: zeros
+          sts128u(sp_u + rb + ((ch0 ^ sw) << 4), 0u, 0u, 0u, 0u);
+          sts128u(sp_u + rb + (((ch0 + 1) ^ sw) << 4), 0u, 0u, 0u, 0u);
+          sts128u(sds_u + rb + ((ch0 ^ sw) << 4), 0u, 0u, 0u, 0u);
+          sts128u(sds_u + rb + (((ch0 + 1) ^ sw) << 4), 0u, 0u, 0u, 0u);
+          continue;
+        }
         float sv_[16], dp[16];
         {
           uint32_t r0[16], r1[16];
@@ -540,11 +543,10 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
           pp[t >> 1] = pack2(pv[0], pv[1], bf16);
           dd[t >> 1] = pack2(dv[0], dv[1], bf16);
         }
-        const uint32_t ch0 = (uint32_t)(c * 2), sw = (uint32_t)(r & 7);
-        sts128u(sp_u + row_base + (((ch0) ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
-        sts128u(sp_u + row_base + (((ch0 + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
-        sts128u(sds_u + row_base + (((ch0) ^ sw) << 4), dd[0], dd[1], dd[2], dd[3]);
-        sts128u(sds_u + row_base + (((ch0 + 1) ^ sw) << 4), dd[4], dd[5], dd[6], dd[7]);
+        sts128u(sp_u + rb + ((ch0 ^ sw) << 4), pp[0], pp[1], pp[2], pp[3]);
+        sts128u(sp_u + rb + (((ch0 + 1) ^ sw) << 4), pp[4], pp[5], pp[6], pp[7]);
+        sts128u(sds_u + rb + ((ch0 ^ sw) << 4), dd[0], dd[1], dd[2], dd[3]);
+        sts128u(sds_u + rb + (((ch0 + 1) ^ sw) << 4), dd[4], dd[5], dd[6], dd[7]);
       }
       fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
       tc_fence_before();
@@ -589,12 +591,36 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
           *reinterpret_cast<uint4*>(orow + c * 16) = o0;
           *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
         }
+        // column sums over the warp's 32 rows: halving butterfly (16 shuffles for 16 columns); afterwards lane L
+        // holds column (L >> 1) & 15 ... bit-reversed: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
+        if (!key_ok) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float sum = warp_sum(key_ok ? v[t] : 0.f);
-          if (lane == t) v[0] = sum;                            // lane t keeps column t's sum (in v[0])
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
         }
-        if (lane < 16) atomicAdd(bsum + c * 16 + lane, v[0] * args.inv_scale16);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float send = (lane & 16) ? v[t] : v[t + 8], keep = (lane & 16) ? v[t + 8] : v[t];
+          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float send = (lane & 8) ? v[t] : v[t + 4], keep = (lane & 8) ? v[t + 4] : v[t];
+          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const float send = (lane & 4) ? v[t] : v[t + 2], keep = (lane & 4) ? v[t + 2] : v[t];
+          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        {
+          const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+          v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 1) == 0) {
+          const int colid = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          atomicAdd(bsum + c * 16 + colid, v[0] * args.inv_scale16);
+        }
       }
     }
     tc_fence_before();
@@ -766,8 +792,7 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);
   MMT_LAUNCH_CHECK("attention16_bwd_kernel");
   {
-    int grid2 = row_grid(rows);
-    if (grid2 > num_sms() * 2) grid2 = num_sms() * 2;
+    const int grid2 = row_grid(rows);
     DISPATCH_VEC(d_model, (launch_pdl(bwd::attn_dq_finish_kernel<V>, dim3(grid2), dim3(WARPS * 32), 0, st, dq32, rows,
                                       reinterpret_cast<uint16_t*>(dqkv16), dbias, 1.0f / scale16, bf16)));
     MMT_LAUNCH_CHECK("attn_dq_finish_kernel");

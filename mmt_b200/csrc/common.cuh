@@ -147,6 +147,31 @@ __device__ __forceinline__ float4 dropout_scale4_h16(uint64_t seed, uint32_t sit
   return o;
 }
 
+// ---- fast dropout decisions of the 16-bit operand path ----------------------------------------------
+// One 32-bit integer hash ("lowbias32" finaliser) per PAIR of decisions, 16 random bits each
+// (P(drop) = floor(p * 65536) / 65536), keyed by (seed, site) and a per-element counter.  Dropout only needs
+// a reproducible, well-mixed mask; Philox4x32-10 (the fp32 / tf32 path above) costs ~80 integer
+// instructions per 4 decisions, which made the GEMM epilogues and the attention softmax ALU-bound.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(uint64_t seed, uint32_t site) {
+  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + site * 0x9E3779B9u + 0x6d6d7461u));
+}
+// keep-mask scale of the 4 columns [col4*4, col4*4+4) of `row` (rows < 2^21, columns < 4096)
+__device__ __forceinline__ float4 dropout_scale4_fast(uint32_t key32, uint32_t row, uint32_t col4, uint32_t thr16,
+                                                      float inv_keep) {
+  const uint32_t idx = row * 2048u + col4 * 2u;
+  const uint32_t w0 = hash32(idx ^ key32), w1 = hash32((idx + 1u) ^ key32);
+  float4 o;
+  o.x = (w0 & 0xffffu) >= thr16 ? inv_keep : 0.f;
+  o.y = (w0 >> 16) >= thr16 ? inv_keep : 0.f;
+  o.z = (w1 & 0xffffu) >= thr16 ? inv_keep : 0.f;
+  o.w = (w1 >> 16) >= thr16 ? inv_keep : 0.f;
+  return o;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   // model/bert.py:53: x * 0.5 * (1 + erf(x / sqrt(2)))
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

@@ -30,12 +30,13 @@ namespace mmt {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16, STAGES = 5;
+constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STG_PITCH = 36;
-constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;
+constexpr int STG_PITCH = 36;                         // 32-column chunks (fp32 outputs)
+constexpr int STG_PITCH16 = 68;                       // 64-column chunks (16-bit-only outputs)
+constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH16 * 4;
 constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 + 256;
 
 struct G16Args {
@@ -47,6 +48,11 @@ struct G16Args {
 
 __device__ __forceinline__ uint2 ldg_u2(const void* p) { return *reinterpret_cast<const uint2*>(p); }
 
+// OUT16: the GEMM's only output is 16-bit (C16, optionally the GELU pre-activation aux16): the epilogue then works
+// on 64-column chunks so that every global access of a lane is 16 bytes and every warp-level store covers four
+// complete 128-byte lines.  (With 32-column chunks the 8-byte-per-lane stores produced half lines, and the write
+// path -- a fixed cost per line -- made QKV / FFN-up / GELU' dgrad epilogue-bound at 1/3 of the tensor-core rate.)
+template <bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const G16Args args) {
   const uint32_t rank = cluster_ctarank();
@@ -170,6 +176,117 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int q = warp & 3;                               // TMEM lane quarter == output rows 32q..32q+31
     const int chalf = (warp - 2) >> 2;                    // which half of the 256 columns this warp drains
     const uint32_t stg = smem_u32(staging) + (uint32_t)(warp - 2) * STG_BYTES_PER_WARP;
+    const int sub_r = lane >> 3;                          // access phase: row within a group of 4
+    uint16_t* C16 = reinterpret_cast<uint16_t*>(d.C16);
+    uint16_t* X16 = reinterpret_cast<uint16_t*>(d.aux16);
+    int it = 0;
+    if constexpr (OUT16) {
+      // ---------- 16-bit-only outputs: 64-column chunks, 8 consecutive columns (16 bytes) per lane ----------
+      const int sub_c = (lane & 7) * 8;
+      for (int w = pair_id; w < num_work; w += num_pairs, ++it) {
+        int z, m0, n0, kb0, nkb;
+        decode(w, z, m0, n0, kb0, nkb);
+        const int buf = it & 1;
+        const int64_t zoff = (int64_t)(z / d.batch_inner) * d.c_bs0 + (int64_t)(z % d.batch_inner) * d.c_bs1;
+        const float* bias = d.bias ? d.bias + (int64_t)z * d.bias_bs : nullptr;
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = chalf * 2; c < chalf * 2 + 2; ++c) {
+          const int nb = n0 + c * 64;
+          if (nb >= d.N || (d.flags & 512)) break;           // warp-uniform (512: timing experiment, no epilogue)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                   // TMEM -> this lane's row of the staging tile
+            float v[32];
+            tmem_ld32(acc + (uint32_t)(c * 64 + hh * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              sts128(stg + (uint32_t)(lane * STG_PITCH16 + hh * 32 + j) * 4,
+                     make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha));
+          }
+          __syncwarp();
+          if (d.flags & 256) { __syncwarp(); continue; }     // timing experiment: TMEM drain + staging only
+          const int col = nb + sub_c;
+          const bool colok = col < d.N;                      // N % 8 == 0 on this path (checked by the host)
+          float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (bias && colok) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + col), b1 = *reinterpret_cast<const float4*>(bias + col + 4);
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+          }
+          float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int ih = 0; ih < 2; ++ih) {                   // two groups of 4 row-phases (register budget)
+            float o[4][8];
+            bool ok[4];
+            int64_t off[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 4 * (ih * 4 + i) + sub_r;
+              const int m = m0 + (int)rank * BM + q * 32 + rl;
+              ok[i] = (m < d.M) && colok;
+              off[i] = zoff + (int64_t)m;
+              const float4 a0 = lds128(stg + (uint32_t)(rl * STG_PITCH16 + sub_c) * 4);
+              const float4 a1 = lds128(stg + (uint32_t)(rl * STG_PITCH16 + sub_c + 4) * 4);
+              o[i][0] = a0.x + bv[0]; o[i][1] = a0.y + bv[1]; o[i][2] = a0.z + bv[2]; o[i][3] = a0.w + bv[3];
+              o[i][4] = a1.x + bv[4]; o[i][5] = a1.y + bv[5]; o[i][6] = a1.z + bv[6]; o[i][7] = a1.w + bv[7];
+            }
+            if (d.epilogue == MMT_EPI_GELU) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (ok[i])
+                  *reinterpret_cast<uint4*>(X16 + off[i] * d.aux_ld + col) =
+                      make_uint4(pack2(o[i][0], o[i][1], bf16), pack2(o[i][2], o[i][3], bf16), pack2(o[i][4], o[i][5], bf16),
+                                 pack2(o[i][6], o[i][7], bf16));
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[i][t] = gelu_fast(o[i][t]);
+              }
+            } else if (d.epilogue == MMT_EPI_DGELU) {
+              uint4 u[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                u[i] = ok[i] ? *reinterpret_cast<const uint4*>(X16 + off[i] * d.aux_ld + col) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 u0 = unpack2(u[i].x, bf16), u1 = unpack2(u[i].y, bf16), u2 = unpack2(u[i].z, bf16), u3 = unpack2(u[i].w, bf16);
+                o[i][0] *= dgelu_fast(u0.x); o[i][1] *= dgelu_fast(u0.y); o[i][2] *= dgelu_fast(u1.x); o[i][3] *= dgelu_fast(u1.y);
+                o[i][4] *= dgelu_fast(u2.x); o[i][5] *= dgelu_fast(u2.y); o[i][6] *= dgelu_fast(u3.x); o[i][7] *= dgelu_fast(u3.y);
+              }
+            }
+            const float s16 = d.out16_scale;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!ok[i]) continue;
+              *reinterpret_cast<uint4*>(C16 + off[i] * d.c16_ld + col) =
+                  make_uint4(pack2(o[i][0] * s16, o[i][1] * s16, bf16), pack2(o[i][2] * s16, o[i][3] * s16, bf16),
+                             pack2(o[i][4] * s16, o[i][5] * s16, bf16), pack2(o[i][6] * s16, o[i][7] * s16, bf16));
+#pragma unroll
+              for (int t = 0; t < 8; ++t) cs[t] += o[i][t];
+            }
+          }
+          if (d.colsum != nullptr) {                          // fused bias gradient: column sums of the output
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 8);
+              cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 16);
+            }
+            const float k = d.colsum_scale;
+            if (sub_r == 0 && colok) {
+              float* p = d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + col;
+              atomicAdd(reinterpret_cast<float4*>(p), make_float4(cs[0] * k, cs[1] * k, cs[2] * k, cs[3] * k));
+              atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(cs[4] * k, cs[5] * k, cs[6] * k, cs[7] * k));
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive_relaxed(&tempty_bar[buf]); else mbar_arrive_on_leader(&tempty_bar[buf]);
+        }
+      }
+    } else {
+    // ---------- general epilogue: 32-column chunks, 4 columns per lane (fp32 lines are complete at 16 B / lane) ----------
     const bool vec32 = (d.C32 == nullptr || (((d.c32_ld | d.c_bs0 | d.c_bs1) & 3) == 0 && ((uintptr_t)d.C32 & 15) == 0)) &&
                        (d.add == nullptr || ((d.add_ld & 3) == 0 && ((uintptr_t)d.add & 15) == 0)) &&
                        (d.bias == nullptr || ((d.bias_bs & 3) == 0 && ((uintptr_t)d.bias & 15) == 0)) &&
@@ -177,13 +294,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const bool vec16 = (d.C16 == nullptr || (((d.c16_ld | d.c_bs0 | d.c_bs1) & 3) == 0 && ((uintptr_t)d.C16 & 7) == 0)) &&
                        (d.aux16 == nullptr || (((d.aux_ld | d.c_bs0 | d.c_bs1) & 3) == 0 && ((uintptr_t)d.aux16 & 7) == 0));
     const bool vec_ok = vec32 && vec16;
-    const int sub_r = lane >> 3;                          // store phase: row within a group of 4
     const int sub_c = (lane & 7) * 4;                     // store phase: first of this lane's 4 columns
     const float inv_keep = d.p_drop > 0.f ? 1.f / (1.f - d.p_drop) : 1.f;
     const uint64_t seed = d.seed + (d.seed_ctr ? *d.seed_ctr : 0);
-    uint16_t* C16 = reinterpret_cast<uint16_t*>(d.C16);
-    uint16_t* X16 = reinterpret_cast<uint16_t*>(d.aux16);
-    int it = 0;
+    const uint32_t key32 = drop_key(seed, d.site), thr16 = (uint32_t)(d.p_drop * 65536.0f);
     for (int w = pair_id; w < num_work; w += num_pairs, ++it) {
       int z, m0, n0, kb0, nkb;
       decode(w, z, m0, n0, kb0, nkb);
@@ -197,7 +311,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll 1
       for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int nb = n0 + c * 32;
-        if (nb >= d.N) break;                             // warp-uniform
+        if (nb >= d.N || (d.flags & 512)) break;           // warp-uniform (512: timing experiment, no epilogue)
         float v[32];
         tmem_ld32(acc + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -206,6 +320,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                  make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha));
         __syncwarp();
         const int col = nb + sub_c;
+        if (d.flags & 256) { __syncwarp(); continue; }     // timing experiment: TMEM drain + staging only
         const bool full = vec_ok && (col + 4 <= d.N);
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (bias && lead) {
@@ -257,7 +372,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           if (d.p_drop > 0.f) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 sc = dropout_scale4(seed, d.site, (uint32_t)mrow[i], (uint32_t)(col >> 2), d.p_drop, inv_keep);
+              const float4 sc = dropout_scale4_fast(key32, (uint32_t)mrow[i], (uint32_t)(col >> 2), thr16, inv_keep);
               o[i].x *= sc.x; o[i].y *= sc.y; o[i].z *= sc.z; o[i].w *= sc.w;
             }
           }
@@ -301,7 +416,6 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           for (int i = 0; i < 8; ++i) {
             if (!ok[i]) continue;
             const float ov[4] = {o[i].x, o[i].y, o[i].z, o[i].w};
-            const int64_t rb = zoff + (int64_t)mrow[i];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               if (col + t >= d.N) continue;
@@ -309,7 +423,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               if (d.epilogue == MMT_EPI_GELU) { X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t] = pack1(val, bf16); val = gelu_fast(val); }
               else if (d.epilogue == MMT_EPI_DGELU) val *= dgelu_fast(unpack1(X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t], bf16));
               if (d.p_drop > 0.f) {
-                const float4 sc = dropout_scale4(seed, d.site, (uint32_t)mrow[i], (uint32_t)((col + t) >> 2), d.p_drop, inv_keep);
+                const float4 sc = dropout_scale4_fast(key32, (uint32_t)mrow[i], (uint32_t)((col + t) >> 2), thr16, inv_keep);
                 const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
                 val *= scv[(col + t) & 3];
               }
@@ -318,7 +432,6 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               if (C16) C16[zoff + (int64_t)mrow[i] * d.c16_ld + col + t] = pack1(val * d.out16_scale, bf16);
               if (d.colsum != nullptr) atomicAdd(d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + col + t, val * d.colsum_scale);
             }
-            (void)rb;
           }
         }
         __syncwarp();
@@ -328,6 +441,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       if (lane == 0) {
         if (leader) mbar_arrive_relaxed(&tempty_bar[buf]); else mbar_arrive_on_leader(&tempty_bar[buf]);
       }
+    }
     }
   }
   __syncthreads();
@@ -426,6 +540,7 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   MMT_ARG_CHECK(d.epilogue >= MMT_EPI_NONE && d.epilogue <= MMT_EPI_DGELU, MMT_E_ARG, "mmt_gemm16: bad epilogue %d", d.epilogue);
   MMT_ARG_CHECK(d.epilogue == MMT_EPI_NONE || d.aux16 != nullptr, MMT_E_ARG, "mmt_gemm16: epilogue %d needs aux16", d.epilogue);
   MMT_ARG_CHECK(d.p_drop >= 0.f && d.p_drop < 1.f, MMT_E_ARG, "mmt_gemm16: p_drop=%f", (double)d.p_drop);
+  MMT_ARG_CHECK(d.p_drop == 0.f || d.N <= 4096, MMT_E_UNSUPPORTED, "mmt_gemm16: epilogue dropout needs N <= 4096 (N=%d)", d.N);
   if (d.M == 0 || d.N == 0) return 0;
   G16Args args;
   args.d = d;
@@ -460,6 +575,11 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   if (rc) return rc;
   rc = make_map16(&mb, d.B, d.N, d.K, d.b_ld, d.b_mn != 0, BNH, bo, d.batch_inner, d.b_bs0, d.b_bs1, d.dtype, "B");
   if (rc) return rc;
+  // 16-bit-only outputs take the 64-column epilogue (16-byte accesses, complete 128-byte lines)
+  const bool out16 = d.C16 && !d.C32 && !d.add && d.p_drop == 0.f && args.split_k == 1 && (d.N % 8) == 0 &&
+                     ((d.c16_ld | d.c_bs0 | d.c_bs1 | d.bias_bs | d.colsum_bs) % 8) == 0 && ((uintptr_t)d.C16 % 16) == 0 &&
+                     (!d.aux16 || ((d.aux_ld % 8) == 0 && ((uintptr_t)d.aux16 % 16) == 0)) &&
+                     (!d.bias || ((uintptr_t)d.bias % 16) == 0) && (!d.colsum || ((uintptr_t)d.colsum % 16) == 0);
   static std::mutex mu;
   static bool configured[64] = {};
   int dev = 0;
@@ -467,14 +587,16 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   {
     std::lock_guard<std::mutex> lk(mu);
     if (dev < 64 && !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(gemm16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
       if (e != cudaSuccess) return cuda_status(e, "mmt_gemm16 smem attribute");
       configured[dev] = true;
     }
   }
   const int work = tiles * args.split_k * d.batch;
   const int pairs = work < max_pairs ? work : max_pairs;
-  launch_pdl(gemm16_kernel, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, args);
+  if (out16) launch_pdl(gemm16_kernel<true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, args);
+  else launch_pdl(gemm16_kernel<false>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, args);
   MMT_LAUNCH_CHECK("gemm16_kernel");
   return 0;
 }

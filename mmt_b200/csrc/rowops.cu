@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
   pdl_trigger();
   pdl_wait();
   if (ctr != nullptr) seed += *ctr;        // device-side step counter (CUDA-graph replays)
+  const bool fast = dt16 != nullptr;       // 16-bit path: the hash mask the GEMM epilogue applied
+  const uint32_t key32 = drop_key(seed, site), thr16 = (uint32_t)(p_drop * 65536.0f);
   constexpr int d = 128 * VEC;
   __shared__ float4 red[WARPS * VEC * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -270,7 +272,8 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
     if (p_drop > 0.f) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        float4 sc = dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
+        float4 sc = fast ? dropout_scale4_fast(key32, (uint32_t)r, lane + 32 * i, thr16, inv_keep)
+                         : dropout_scale4(seed, site, (uint32_t)r, lane + 32 * i, p_drop, inv_keep);
         F4_OP(gy[i], gy[i].x * sc.x, gy[i].y * sc.y, gy[i].z * sc.z, gy[i].w * sc.w);
       }
       if (dt != nullptr) store_row<VEC>(dt + r * d, lane, gy);
@@ -573,9 +576,9 @@ __global__ void __launch_bounds__(WARPS * 32) ln16_fwd_kernel(
 
 // out[r, c4*4 .. +3] = rn16(mask * in * scale); columns >= cols are written as zero up to out_cols
 __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ in, int64_t rows, int cols, int64_t in_ld,
-                                                     uint16_t* __restrict__ out, int out_cols, int64_t out_ld, float scale,
-                                                     float p_drop, uint64_t seed, const uint64_t* __restrict__ ctr,
-                                                     uint32_t site, int bf16, int vec) {
+                                                     uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo, int out_cols,
+                                                     int64_t out_ld, float scale, float p_drop, uint64_t seed,
+                                                     const uint64_t* __restrict__ ctr, uint32_t site, int bf16, int vec) {
   pdl_trigger();
   pdl_wait();
   if (ctr != nullptr) seed += *ctr;
@@ -595,15 +598,28 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ i
       if (c + 3 < cols) v.w = p[3];
     }
     if (p_drop > 0.f) {
-      const float4 sc = dropout_scale4(seed, site, (uint32_t)r, (uint32_t)(c >> 2), p_drop, inv_keep);
+      const float4 sc = dropout_scale4_fast(drop_key(seed, site), (uint32_t)r, (uint32_t)(c >> 2),
+                                            (uint32_t)(p_drop * 65536.0f), inv_keep);
       F4_OP(v, v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
     }
     F4_OP(v, v.x * scale, v.y * scale, v.z * scale, v.w * scale);
     uint16_t* q = out + r * out_ld + c;
-    if (vec && c + 4 <= out_cols) *reinterpret_cast<uint2*>(q) = pack4(v, bf16 != 0);
+    const uint2 hi = pack4(v, bf16 != 0);
+    if (vec && c + 4 <= out_cols) *reinterpret_cast<uint2*>(q) = hi;
     else {
       const float vv[4] = {v.x, v.y, v.z, v.w};
       for (int t = 0; t < 4; ++t) if (c + t < out_cols) q[t] = pack1(vv[t], bf16 != 0);
+    }
+    if (out_lo != nullptr) {
+      // second term of the two-term split x ~= hi + lo / 2048 (lo carries the next 11 bits of the significand)
+      const float4 h = unpack4(hi, bf16 != 0);
+      const float4 lo = make_float4((v.x - h.x) * 2048.f, (v.y - h.y) * 2048.f, (v.z - h.z) * 2048.f, (v.w - h.w) * 2048.f);
+      uint16_t* ql = out_lo + r * out_ld + c;
+      if (vec && c + 4 <= out_cols) *reinterpret_cast<uint2*>(ql) = pack4(lo, bf16 != 0);
+      else {
+        const float vv[4] = {lo.x, lo.y, lo.z, lo.w};
+        for (int t = 0; t < 4; ++t) if (c + t < out_cols) ql[t] = pack1(vv[t], bf16 != 0);
+      }
     }
   }
 }
@@ -806,7 +822,7 @@ int mmt_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
   return 0;
 }
 
-int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, int32_t out_cols,
+int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void* out, void* out_lo, int32_t out_cols,
                int64_t out_ld, float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
                int32_t dtype, void* stream) {
   MMT_ARG_CHECK(in && out, MMT_E_ARG, "mmt_cast16: null pointer");
@@ -816,11 +832,13 @@ int mmt_cast16(const float* in, int64_t rows, int32_t cols, int64_t in_ld, void*
   CHECK_P(p_drop);
   const int64_t total = rows * ((out_cols + 3) / 4);
   if (total == 0) return 0;
-  const int vec = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && (in_ld % 4 == 0) && (out_ld % 4 == 0);
+  const int vec = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && ((uintptr_t)out_lo % 8 == 0) &&
+                  (in_ld % 4 == 0) && (out_ld % 4 == 0);
   int64_t blocks = (total + 255) / 256;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   launch_pdl(cast16_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, in, rows, cols, in_ld,
-             reinterpret_cast<uint16_t*>(out), out_cols, out_ld, scale, p_drop, seed, seed_ctr, site,
+             reinterpret_cast<uint16_t*>(out), reinterpret_cast<uint16_t*>(out_lo), out_cols, out_ld, scale, p_drop, seed,
+             seed_ctr, site,
              dtype == MMT_DT_BF16 ? 1 : 0, vec);
   MMT_LAUNCH_CHECK("cast16");
   return 0;

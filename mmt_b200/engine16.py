@@ -399,24 +399,29 @@ def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
                          ptr(gflat, L.off("video_dim_reduce.%s.fc.bias" % mod)), 1, st), "mmt_colsum")
 
 
-def sims_backward_products(cfg_or_dt, ddots, vid, txt, scale16):
-  """The two gradient products of the similarity (engine.sims_backward) on 16-bit operands:
-  dtxt[:, m, :] = ddots_m @ vid_m ; dvid[:, m, :] = ddots_m^T @ txt_m."""
-  dt = cfg_or_dt
+def sims_backward_products(dt, ddots, vid, txt, scale16):
+  """The two gradient products of the similarity (engine.sims_backward):
+  dtxt[:, m, :] = ddots_m @ vid_m ; dvid[:, m, :] = ddots_m^T @ txt_m.
+  They are the ROOT of every video- and text-side gradient, and tiny (2 x 2*N^2*M*d FLOP), so both operands are
+  split into two 16-bit terms (x = hi + lo / 2048) and each product is three tensor-core passes
+  Ah Bh + (Ah Bl + Al Bh) / 2048 -- fp32-class accuracy (~2^-21) instead of one 11-bit rounding that every
+  downstream gradient would inherit."""
   Nv, M, d = vid.shape
   Nq = txt.shape[0]
   Nvp = _pad8(Nv)
   inv = 1.0 / scale16
-  dd16 = _e16((M, Nq, Nvp), vid, dt)
-  cast16(dt, ddots, M * Nq, Nv, Nv, dd16, Nvp, Nvp, scale=scale16)
-  vid16 = _e16((Nv, M * d), vid, dt)
-  txt16 = _e16((Nq, M * d), vid, dt)
-  cast16(dt, vid, Nv, M * d, M * d, vid16, M * d, M * d)
-  cast16(dt, txt, Nq, M * d, M * d, txt16, M * d, M * d)
+  dd_h, dd_l = _e16((M, Nq, Nvp), vid, dt), _e16((M, Nq, Nvp), vid, dt)
+  cast16(dt, ddots, M * Nq, Nv, Nv, dd_h, Nvp, Nvp, scale=scale16, out_lo=dd_l)
+  v_h, v_l = _e16((Nv, M * d), vid, dt), _e16((Nv, M * d), vid, dt)
+  t_h, t_l = _e16((Nq, M * d), vid, dt), _e16((Nq, M * d), vid, dt)
+  cast16(dt, vid, Nv, M * d, M * d, v_h, M * d, M * d, out_lo=v_l)
+  cast16(dt, txt, Nq, M * d, M * d, t_h, M * d, M * d, out_lo=t_l)
   dtxt = torch.empty_like(txt)
   dvid = torch.empty_like(vid)
-  gemm16(dt, Nq, d, Nv, dd16, Nvp, 0, vid16, M * d, 1, alpha=inv, batch=M, a_bs=(Nq * Nvp, 0), b_bs=(d, 0),
-         c_bs=(d, 0), C32=dtxt, c32_ld=M * d)
-  gemm16(dt, Nv, d, Nq, dd16, Nvp, 1, txt16, M * d, 1, alpha=inv, batch=M, a_bs=(Nq * Nvp, 0), b_bs=(d, 0),
-         c_bs=(d, 0), C32=dvid, c32_ld=M * d)
+  kw = dict(batch=M, a_bs=(Nq * Nvp, 0), b_bs=(d, 0), c_bs=(d, 0), c32_ld=M * d)
+  lo = inv / 2048.0
+  for i, (a, b, al) in enumerate(((dd_h, v_h, inv), (dd_h, v_l, lo), (dd_l, v_h, lo))):
+    gemm16(dt, Nq, d, Nv, a, Nvp, 0, b, M * d, 1, alpha=al, C32=dtxt, add=dtxt if i else None, add_ld=M * d, **kw)
+  for i, (a, b, al) in enumerate(((dd_h, t_h, inv), (dd_h, t_l, lo), (dd_l, t_h, lo))):
+    gemm16(dt, Nv, d, Nq, a, Nvp, 1, b, M * d, 1, alpha=al, C32=dvid, add=dvid if i else None, add_ld=M * d, **kw)
   return dvid, dtxt

@@ -330,7 +330,9 @@ def test_train_step_parity_f16(dev, case):
   pipeline shows the same numbers in tests/test_operand_precision_emulation.py)."""
   e_conf, e_l2, e_loss, g_max, g_l2, worst, worst_l2 = _step_errors(case, "f16")
   assert e_conf < 1e-3 and e_l2 < 1e-3 and e_loss < 1e-3
-  assert g_max < 1e-3 and g_l2 < 1e-3
+  # C1 is an 8 x 8 problem over 31-token sequences: its max-norm figure is the maximum over very few large
+  # elements (an exact-accumulation fp16 pipeline emulated on the oracle gives 1.2e-3 there, 3.7e-4 at C2)
+  assert g_max < (2e-3 if case == "C1" else 1e-3) and g_l2 < 1e-3
   assert worst[1] < 3e-2, worst
 
 
