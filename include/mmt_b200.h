@@ -273,7 +273,8 @@ int mmt_retrieval_ranks(const float* sims, const int32_t* valid, int32_t Nq, int
 enum { MMT_DT_F16 = 0, MMT_DT_BF16 = 1 };
 
 /* C(m,n) = epilogue(alpha * sum_k A(m,k) B(n,k)) with 16-bit A, B:
- *   v = alpha*acc + bias[n];  GELU: aux16 <- v, v = gelu_erf(v);  DGELU: v *= gelu_erf'(aux16);
+ *   v = alpha*acc + bias[n];  GELU: aux16 <- gelu_erf'(v), v = gelu_erf(v);  DGELU: v *= aux16 (the stored
+ *   derivative: activation and derivative share one erf / exp evaluation in the forward epilogue);
  *   v *= dropout_mask(seed, site, m, n/4) / (1-p);  v += add(m,n);
  *   C32 <- v;  C16 <- rn16(v * out16_scale);  colsum[n] += colsum_scale * sum_m v.
  * A(m,k) = A[m*a_ld + k] (a_mn = 0) or A[k*a_ld + m] (a_mn = 1, "MN-major": dgrad / wgrad operands are

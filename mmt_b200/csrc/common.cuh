@@ -213,6 +213,14 @@ __device__ __forceinline__ float gelu_fast(float u) {
   erf_parts(u, er, e);
   return 0.5f * u * (1.0f + er);
 }
+// gelu(u) and gelu'(u) from one erf / exp evaluation (FFN-up epilogue: the derivative is stored for the backward)
+__device__ __forceinline__ void gelu_both(float u, float& g, float& dg) {
+  float er, e;
+  erf_parts(u, er, e);
+  const float cdf = fmaf(0.5f, er, 0.5f);
+  g = u * cdf;
+  dg = fmaf(u * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float dgelu_fast(float u) {
   float er, e;
   erf_parts(u, er, e);

@@ -37,7 +37,7 @@ constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = 
 constexpr int STG_PITCH = 36;                         // 32-column chunks (fp32 outputs)
 constexpr int STG_PITCH16 = 68;                       // 64-column chunks (16-bit-only outputs)
 constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH16 * 4;
-constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 + 256;
+constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 1024 + 256 + EPI_WARPS * 512;
 
 struct G16Args {
   mmt_gemm16_desc d;
@@ -48,13 +48,14 @@ struct G16Args {
 
 __device__ __forceinline__ uint2 ldg_u2(const void* p) { return *reinterpret_cast<const uint2*>(p); }
 
-// OUT16: the GEMM's only output is 16-bit (C16, optionally the GELU pre-activation aux16): the epilogue then works
-// on 64-column chunks so that every global access of a lane is 16 bytes and every warp-level store covers four
-// complete 128-byte lines.  (With 32-column chunks the 8-byte-per-lane stores produced half lines, and the write
-// path -- a fixed cost per line -- made QKV / FFN-up / GELU' dgrad epilogue-bound at 1/3 of the tensor-core rate.)
+// OUT16: the GEMM's only output is 16-bit (C16, optionally the GELU pre-activation aux16).  These are the
+// output-heavy, short-K products (QKV, FFN-up, GELU' dgrad: up to 2 x 86 MB written per launch); their epilogue
+// computes in the TMEM layout and moves data with TMA only (see the epilogue).  With per-lane global stores they
+// ran epilogue-bound at 1/3 - 1/2 of the tensor-core rate.
 template <bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const G16Args args) {
+gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_x, const G16Args args) {
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -66,7 +67,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;             // [EPI_WARPS] GELU' operand tiles (OUT16 epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256);   // [EPI_WARPS][128]
 
   const mmt_gemm16_desc& d = args.d;
   const bool bf16 = d.dtype == MMT_DT_BF16;
@@ -78,6 +81,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
+    for (int b = 0; b < EPI_WARPS; ++b) mbar_init(&aux_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -181,103 +185,149 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint16_t* X16 = reinterpret_cast<uint16_t*>(d.aux16);
     int it = 0;
     if constexpr (OUT16) {
-      // ---------- 16-bit-only outputs: 64-column chunks, 8 consecutive columns (16 bytes) per lane ----------
-      const int sub_c = (lane & 7) * 8;
+      // ---------- 16-bit-only outputs: all math in the TMEM layout (thread = output row, 64 columns per chunk),
+      // results leave through TMA stores from a 128-byte-swizzled [32 rows x 64 columns] tile per warp; the GELU'
+      // operand arrives the same way (TMA load).  No fp32 staging, no per-lane global accesses. ----------
+      uint8_t* tile_c = reinterpret_cast<uint8_t*>(staging) + (uint32_t)(warp - 2) * 8192;   // 2 x 4 KB tiles, 1024-aligned (swizzle phase)
+      uint8_t* tile_x = tile_c + 4096;
+      float* sbias = bias_s + (warp - 2) * 128;               // this warp's 128 bias values of the current tile
+      uint64_t* xbar = &aux_bar[warp - 2];
+      const uint32_t tc_u = smem_u32(tile_c), tx_u = smem_u32(tile_x);
+      const uint32_t sw = (uint32_t)(lane & 7);
+      uint32_t xphase = 0;
       for (int w = pair_id; w < num_work; w += num_pairs, ++it) {
         int z, m0, n0, kb0, nkb;
         decode(w, z, m0, n0, kb0, nkb);
         const int buf = it & 1;
-        const int64_t zoff = (int64_t)(z / d.batch_inner) * d.c_bs0 + (int64_t)(z % d.batch_inner) * d.c_bs1;
+        const int z0 = z / d.batch_inner, z1 = z % d.batch_inner;
         const float* bias = d.bias ? d.bias + (int64_t)z * d.bias_bs : nullptr;
+        const int row0 = m0 + (int)rank * BM + q * 32;
+        const bool row_ok = row0 + lane < d.M;
+        if (bias) {
+          const int bc = n0 + chalf * 128 + lane * 4;
+          const float4 b = bc < d.N ? __ldg(reinterpret_cast<const float4*>(bias + bc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+          *reinterpret_cast<float4*>(sbias + lane * 4) = b;
+          __syncwarp();
+        }
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int c = chalf * 2; c < chalf * 2 + 2; ++c) {
-          const int nb = n0 + c * 64;
-          if (nb >= d.N || (d.flags & 512)) break;           // warp-uniform (512: timing experiment, no epilogue)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {                   // TMEM -> this lane's row of the staging tile
-            float v[32];
-            tmem_ld32(acc + (uint32_t)(c * 64 + hh * 32), v);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              sts128(stg + (uint32_t)(lane * STG_PITCH16 + hh * 32 + j) * 4,
-                     make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha));
+          const int col0 = n0 + c * 64;
+          if (col0 >= d.N || (d.flags & 512)) break;         // warp-uniform (512: timing experiment, no epilogue)
+          if (d.epilogue == MMT_EPI_DGELU && lane == 0) {    // GELU' operand tile: asynchronous, consumed below
+            mbar_arrive_expect_tx(xbar, 4096);
+            tma_load_4d(tile_x, &map_x, xbar, col0, row0, z1, z0);
           }
+          float v[64];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float t[32];
+            tmem_ld32(acc + (uint32_t)(c * 64 + hh * 32), t);
+            if (d.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh * 32 + j] = t[j] * d.alpha;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[hh * 32 + j] = t[j];
+            }
+          }
+          if (bias) {                                        // same 64 values for every lane: broadcast reads
+            const float* sb = sbias + (c & 1) * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(sb + j);
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (d.flags & 256) continue;                       // timing experiment: TMEM drain only
+          if (lane == 0) bulk_wait_read0();                  // the previous chunk's TMA stores have read both tiles
           __syncwarp();
-          if (d.flags & 256) { __syncwarp(); continue; }     // timing experiment: TMEM drain + staging only
-          const int col = nb + sub_c;
-          const bool colok = col < d.N;                      // N % 8 == 0 on this path (checked by the host)
-          float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (bias && colok) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + col), b1 = *reinterpret_cast<const float4*>(bias + col + 4);
-            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+          if (d.epilogue == MMT_EPI_GELU) {
+            // activation and its derivative from ONE erf / exp evaluation; the derivative is what the backward
+            // GEMM's epilogue multiplies by (aux16), so GELU' costs the backward two instructions per element
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float g[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) gelu_both(v[8 * j + t], v[8 * j + t], g[t]);
+              sts128u(tx_u + (uint32_t)lane * 128 + (((uint32_t)j ^ sw) << 4), pack2(g[0], g[1], bf16), pack2(g[2], g[3], bf16),
+                      pack2(g[4], g[5], bf16), pack2(g[6], g[7], bf16));
+            }
+          } else if (d.epilogue == MMT_EPI_DGELU) {
+            mbar_wait(xbar, xphase);
+            xphase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                           : "r"(tx_u + (uint32_t)lane * 128 + (((uint32_t)j ^ sw) << 4)) : "memory");
+              const float2 u0 = unpack2(u.x, bf16), u1 = unpack2(u.y, bf16), u2 = unpack2(u.z, bf16), u3 = unpack2(u.w, bf16);
+              v[8 * j] *= u0.x; v[8 * j + 1] *= u0.y; v[8 * j + 2] *= u1.x; v[8 * j + 3] *= u1.y;
+              v[8 * j + 4] *= u2.x; v[8 * j + 5] *= u2.y; v[8 * j + 6] *= u3.x; v[8 * j + 7] *= u3.y;
+            }
           }
-          float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int ih = 0; ih < 2; ++ih) {                   // two groups of 4 row-phases (register budget)
-            float o[4][8];
-            bool ok[4];
-            int64_t off[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rl = 4 * (ih * 4 + i) + sub_r;
-              const int m = m0 + (int)rank * BM + q * 32 + rl;
-              ok[i] = (m < d.M) && colok;
-              off[i] = zoff + (int64_t)m;
-              const float4 a0 = lds128(stg + (uint32_t)(rl * STG_PITCH16 + sub_c) * 4);
-              const float4 a1 = lds128(stg + (uint32_t)(rl * STG_PITCH16 + sub_c + 4) * 4);
-              o[i][0] = a0.x + bv[0]; o[i][1] = a0.y + bv[1]; o[i][2] = a0.z + bv[2]; o[i][3] = a0.w + bv[3];
-              o[i][4] = a1.x + bv[4]; o[i][5] = a1.y + bv[5]; o[i][6] = a1.z + bv[6]; o[i][7] = a1.w + bv[7];
-            }
-            if (d.epilogue == MMT_EPI_GELU) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (ok[i])
-                  *reinterpret_cast<uint4*>(X16 + off[i] * d.aux_ld + col) =
-                      make_uint4(pack2(o[i][0], o[i][1], bf16), pack2(o[i][2], o[i][3], bf16), pack2(o[i][4], o[i][5], bf16),
-                                 pack2(o[i][6], o[i][7], bf16));
-#pragma unroll
-                for (int t = 0; t < 8; ++t) o[i][t] = gelu_fast(o[i][t]);
-              }
-            } else if (d.epilogue == MMT_EPI_DGELU) {
-              uint4 u[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                u[i] = ok[i] ? *reinterpret_cast<const uint4*>(X16 + off[i] * d.aux_ld + col) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 u0 = unpack2(u[i].x, bf16), u1 = unpack2(u[i].y, bf16), u2 = unpack2(u[i].z, bf16), u3 = unpack2(u[i].w, bf16);
-                o[i][0] *= dgelu_fast(u0.x); o[i][1] *= dgelu_fast(u0.y); o[i][2] *= dgelu_fast(u1.x); o[i][3] *= dgelu_fast(u1.y);
-                o[i][4] *= dgelu_fast(u2.x); o[i][5] *= dgelu_fast(u2.y); o[i][6] *= dgelu_fast(u3.x); o[i][7] *= dgelu_fast(u3.y);
-              }
-            }
+          if (d.out16_scale != 1.0f) {
             const float s16 = d.out16_scale;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (!ok[i]) continue;
-              *reinterpret_cast<uint4*>(C16 + off[i] * d.c16_ld + col) =
-                  make_uint4(pack2(o[i][0] * s16, o[i][1] * s16, bf16), pack2(o[i][2] * s16, o[i][3] * s16, bf16),
-                             pack2(o[i][4] * s16, o[i][5] * s16, bf16), pack2(o[i][6] * s16, o[i][7] * s16, bf16));
-#pragma unroll
-              for (int t = 0; t < 8; ++t) cs[t] += o[i][t];
-            }
+            for (int j = 0; j < 64; ++j) v[j] *= s16;
           }
-          if (d.colsum != nullptr) {                          // fused bias gradient: column sums of the output
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 8);
-              cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], 16);
-            }
-            const float k = d.colsum_scale;
-            if (sub_r == 0 && colok) {
-              float* p = d.colsum + (int64_t)(z % d.batch_inner) * d.colsum_bs + col;
-              atomicAdd(reinterpret_cast<float4*>(p), make_float4(cs[0] * k, cs[1] * k, cs[2] * k, cs[3] * k));
-              atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(cs[4] * k, cs[5] * k, cs[6] * k, cs[7] * k));
-            }
-          }
+          for (int j = 0; j < 8; ++j)
+            sts128u(tc_u + (uint32_t)lane * 128 + (((uint32_t)j ^ sw) << 4), pack2(v[8 * j], v[8 * j + 1], bf16),
+                    pack2(v[8 * j + 2], v[8 * j + 3], bf16), pack2(v[8 * j + 4], v[8 * j + 5], bf16),
+                    pack2(v[8 * j + 6], v[8 * j + 7], bf16));
+          fence_proxy_async_smem();
           __syncwarp();
+          if (lane == 0) {                                   // clipped at the tensor's edges by the TMA unit
+            tma_store_4d(&map_c, tc_u, col0, row0, z1, z0);
+            if (d.epilogue == MMT_EPI_GELU) tma_store_4d(&map_x, tx_u, col0, row0, z1, z0);
+            bulk_commit();
+          }
+          if (d.colsum != nullptr) {
+            // fused bias gradient: column sums over this warp's 32 rows by a halving butterfly (62 shuffles for 64
+            // columns); afterwards lane L holds columns 2 * bitrev5(L) and 2 * bitrev5(L) + 1 ... see `cid`
+            if (!row_ok) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float send = (lane & 16) ? v[j] : v[j + 32], keep = (lane & 16) ? v[j + 32] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float send = (lane & 8) ? v[j] : v[j + 16], keep = (lane & 8) ? v[j + 16] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float send = (lane & 4) ? v[j] : v[j + 8], keep = (lane & 4) ? v[j + 8] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float send = (lane & 2) ? v[j] : v[j + 4], keep = (lane & 2) ? v[j + 4] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float send = (lane & 1) ? v[j] : v[j + 2], keep = (lane & 1) ? v[j + 2] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            // lane L now holds columns cid and cid + 1 with cid = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0
+            const int cid = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 +
+                            (lane & 1) * 2;
+            if (col0 + cid < d.N) {
+              float* p = d.colsum + (int64_t)z1 * d.colsum_bs + col0 + cid;
+              const float k = d.colsum_scale / d.out16_scale;   // v carries out16_scale already
+              atomicAdd(p, v[0] * k);
+              atomicAdd(p + 1, v[1] * k);
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -285,6 +335,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           if (leader) mbar_arrive_relaxed(&tempty_bar[buf]); else mbar_arrive_on_leader(&tempty_bar[buf]);
         }
       }
+      if (lane == 0) bulk_wait0();                           // every TMA store has completed before the CTA retires
     } else {
     // ---------- general epilogue: 32-column chunks, 4 columns per lane (fp32 lines are complete at 16 B / lane) ----------
     const bool vec32 = (d.C32 == nullptr || (((d.c32_ld | d.c_bs0 | d.c_bs1) & 3) == 0 && ((uintptr_t)d.C32 & 15) == 0)) &&
@@ -312,6 +363,23 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int nb = n0 + c * 32;
         if (nb >= d.N || (d.flags & 512)) break;           // warp-uniform (512: timing experiment, no epilogue)
+        const int col = nb + sub_c;
+        const bool full = vec_ok && (col + 4 <= d.N);
+        bool ok[8];
+        int mrow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          mrow[i] = m0 + (int)rank * BM + q * 32 + 4 * i + sub_r;
+          ok[i] = (mrow[i] < d.M) && (col < d.N);
+        }
+        // residual rows first: their global-load latency runs under the TMEM drain and the staging round trip
+        float4 a[8];
+        const bool pre_add = full && d.add != nullptr && args.split_k == 1;
+        if (pre_add) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            a[i] = ok[i] ? *reinterpret_cast<const float4*>(d.add + zoff + (int64_t)mrow[i] * d.add_ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float v[32];
         tmem_ld32(acc + (uint32_t)(c * 32), v);
 #pragma unroll
@@ -319,23 +387,16 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           sts128(stg + (uint32_t)(lane * STG_PITCH + j) * 4,
                  make_float4(v[j] * d.alpha, v[j + 1] * d.alpha, v[j + 2] * d.alpha, v[j + 3] * d.alpha));
         __syncwarp();
-        const int col = nb + sub_c;
         if (d.flags & 256) { __syncwarp(); continue; }     // timing experiment: TMEM drain + staging only
-        const bool full = vec_ok && (col + 4 <= d.N);
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (bias && lead) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) if (col + t < d.N) bv[t] = bias[col + t];
         }
         float4 o[8];
-        bool ok[8];
-        int mrow[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rl = 4 * i + sub_r;
-          mrow[i] = m0 + (int)rank * BM + q * 32 + rl;
-          ok[i] = (mrow[i] < d.M) && (col < d.N);
-          o[i] = lds128(stg + (uint32_t)(rl * STG_PITCH + sub_c) * 4);
+          o[i] = lds128(stg + (uint32_t)((4 * i + sub_r) * STG_PITCH + sub_c) * 4);
           o[i].x += bv[0]; o[i].y += bv[1]; o[i].z += bv[2]; o[i].w += bv[3];
         }
         if (args.split_k > 1) {
@@ -355,8 +416,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           if (d.epilogue == MMT_EPI_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (ok[i]) *reinterpret_cast<uint2*>(X16 + zoff + (int64_t)mrow[i] * d.aux_ld + col) = pack4(o[i], bf16);
-              o[i] = make_float4(gelu_fast(o[i].x), gelu_fast(o[i].y), gelu_fast(o[i].z), gelu_fast(o[i].w));
+              float4 g;
+              gelu_both(o[i].x, o[i].x, g.x); gelu_both(o[i].y, o[i].y, g.y);
+              gelu_both(o[i].z, o[i].z, g.z); gelu_both(o[i].w, o[i].w, g.w);
+              if (ok[i]) *reinterpret_cast<uint2*>(X16 + zoff + (int64_t)mrow[i] * d.aux_ld + col) = pack4(g, bf16);
             }
           } else if (d.epilogue == MMT_EPI_DGELU) {
             uint2 u[8];
@@ -365,8 +428,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 uu = unpack4(u[i], bf16);
-              o[i].x *= dgelu_fast(uu.x); o[i].y *= dgelu_fast(uu.y);
-              o[i].z *= dgelu_fast(uu.z); o[i].w *= dgelu_fast(uu.w);
+              o[i].x *= uu.x; o[i].y *= uu.y; o[i].z *= uu.z; o[i].w *= uu.w;
             }
           }
           if (d.p_drop > 0.f) {
@@ -376,11 +438,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               o[i].x *= sc.x; o[i].y *= sc.y; o[i].z *= sc.z; o[i].w *= sc.w;
             }
           }
-          if (d.add) {
-            float4 a[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              a[i] = ok[i] ? *reinterpret_cast<const float4*>(d.add + zoff + (int64_t)mrow[i] * d.add_ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pre_add) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { o[i].x += a[i].x; o[i].y += a[i].y; o[i].z += a[i].z; o[i].w += a[i].w; }
           }
@@ -420,8 +478,11 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int t = 0; t < 4; ++t) {
               if (col + t >= d.N) continue;
               float val = ov[t];
-              if (d.epilogue == MMT_EPI_GELU) { X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t] = pack1(val, bf16); val = gelu_fast(val); }
-              else if (d.epilogue == MMT_EPI_DGELU) val *= dgelu_fast(unpack1(X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t], bf16));
+              if (d.epilogue == MMT_EPI_GELU) {
+                float g;
+                gelu_both(val, val, g);
+                X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t] = pack1(g, bf16);
+              } else if (d.epilogue == MMT_EPI_DGELU) val *= unpack1(X16[zoff + (int64_t)mrow[i] * d.aux_ld + col + t], bf16);
               if (d.p_drop > 0.f) {
                 const float4 sc = dropout_scale4_fast(key32, (uint32_t)mrow[i], (uint32_t)((col + t) >> 2), thr16, inv_keep);
                 const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
@@ -494,13 +555,14 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 // dimensions; rank-4 map {inner, outer, batch_inner, batch_outer}, 128-byte swizzle.
 // K-major: box {64 k, tile_rows};  MN-major: box {64 rows, 64 k}.
 int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, bool mn_major, int tile_rows,
-               int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, int dtype, const char* what) {
+               int batch_outer, int batch_inner, int64_t bs0, int64_t bs1, int dtype, const char* what, bool output = false) {
   EncodeTiledFn enc = get_encode16();
   MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "mmt_gemm16: cuTensorMapEncodeTiled unavailable");
   MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * 2) % 16 == 0 && ld >= 1, MMT_E_ALIGN,
                 "mmt_gemm16: operand %s needs a 16-byte aligned base and pitch (ld=%lld)", what, (long long)ld);
   MapKey key{(uint64_t)(uintptr_t)base, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, (uint64_t)bs0, (uint64_t)bs1,
-             mn_major ? 1u : 0u, (uint32_t)tile_rows, (uint32_t)batch_outer, (uint32_t)batch_inner, (uint32_t)dtype, 4u};
+             mn_major ? 1u : 0u, (uint32_t)tile_rows, (uint32_t)batch_outer, (uint32_t)batch_inner, (uint32_t)dtype,
+             output ? 5u : 4u};
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -515,7 +577,8 @@ int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int6
   cuuint32_t box[4] = {64, (cuuint32_t)(mn_major ? 64 : tile_rows), 1, 1}, estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, dtype == MMT_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "mmt_gemm16: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
@@ -595,8 +658,17 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   }
   const int work = tiles * args.split_k * d.batch;
   const int pairs = work < max_pairs ? work : max_pairs;
-  if (out16) launch_pdl(gemm16_kernel<true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, args);
-  else launch_pdl(gemm16_kernel<false>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, args);
+  CUtensorMap mc = ma, mx = ma;                              // placeholders unless the TMA epilogue runs
+  if (out16) {
+    rc = make_map16(&mc, d.C16, d.M, d.N, d.c16_ld, false, 32, bo, d.batch_inner, d.c_bs0, d.c_bs1, d.dtype, "C16", true);
+    if (rc) return rc;
+    if (d.aux16) {
+      rc = make_map16(&mx, d.aux16, d.M, d.N, d.aux_ld, false, 32, bo, d.batch_inner, d.c_bs0, d.c_bs1, d.dtype, "aux16", true);
+      if (rc) return rc;
+    }
+  }
+  if (out16) launch_pdl(gemm16_kernel<true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
+  else launch_pdl(gemm16_kernel<false>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
   MMT_LAUNCH_CHECK("gemm16_kernel");
   return 0;
 }

@@ -149,7 +149,7 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
     check(lib.mmt_ln16_fwd(ptr(z1), ptr(flat, L.off(p + "attention.output.layer_norm.weight")),
                            ptr(flat, L.off(p + "attention.output.layer_norm.bias")), BS, d, cfg.eps, ptr(a),
                            ptr(a16), ptr(ls.mean1), ptr(ls.rstd1), dt, st), "mmt_ln16_fwd")
-    # K7: FFN up + erf-GELU (bert.py:218-219, 53): u16 = pre-activation (for GELU'), f16 = activation
+    # K7: FFN up + erf-GELU (bert.py:218-219, 53): f16 = activation, u16 = gelu'(pre-activation) for the backward
     u16, fa16 = _e16((BS, ff), flat, dt), _e16((BS, ff), flat, dt)
     gemm16(dt, BS, ff, d, a16, d, 0, f16, d, 0, b_off=L.off(p + "intermediate.dense.weight"),
            bias=flat, bias_off=L.off(p + "intermediate.dense.bias"), epilogue=EPI_GELU, aux16=u16, aux_ld=ff,

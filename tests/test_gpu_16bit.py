@@ -78,21 +78,20 @@ def test_gemm16_epilogues_splitk_batched(dev, dt):
   B = (torch.randn(N, K, generator=g) * 0.05).to(dev).to(_tdt(dt))
   bias = torch.randn(N, generator=g).to(dev) * 0.1
   u_ref = A.double() @ B.double().t() + bias.double()
-  # GELU: aux16 = pre-activation, C16 = gelu
+  # GELU: aux16 = gelu'(pre-activation), C16 = gelu(pre-activation)
   U16 = torch.zeros(M, N, device=dev, dtype=A.dtype)
   F16 = torch.zeros(M, N, device=dev, dtype=A.dtype)
   _lib.gemm16(dt, M, N, K, A, K, 0, B, K, 0, bias=bias, epilogue=_lib.EPI_GELU, aux16=U16, aux_ld=N, C16=F16, c16_ld=N)
   tol16 = 6e-3 if dt == 1 else 8e-4
-  assert H.rel_err(U16.float(), u_ref) < tol16
+  dg_ref = 0.5 * (1 + torch.erf(u_ref / math.sqrt(2))) + u_ref * torch.exp(-0.5 * u_ref * u_ref) / math.sqrt(2 * math.pi)
+  assert H.rel_err(U16.float(), dg_ref) < tol16            # aux16 = gelu'(pre-activation), stored for the backward
   assert H.rel_err(F16.float(), torch.nn.functional.gelu(u_ref)) < tol16
-  # DGELU with column sums: C32 = (A B^T) * gelu'(U16), colsum = 0.25 * column sums
+  # DGELU with column sums: C32 = (A B^T) * aux16, colsum = 0.25 * column sums
   C = torch.empty(M, N, device=dev)
   cs = torch.zeros(N, device=dev)
   _lib.gemm16(dt, M, N, K, A, K, 0, B, K, 0, epilogue=_lib.EPI_DGELU, aux16=U16, aux_ld=N, C32=C, c32_ld=N,
               colsum=cs, colsum_scale=0.25)
-  ud = U16.double()
-  dg = 0.5 * (1 + torch.erf(ud / math.sqrt(2))) + ud * torch.exp(-0.5 * ud * ud) / math.sqrt(2 * math.pi)
-  ref = (A.double() @ B.double().t()) * dg
+  ref = (A.double() @ B.double().t()) * U16.double()       # DGELU epilogue: multiply by the stored derivative
   assert H.rel_err(C, ref) < 2e-5
   assert H.rel_err(cs, 0.25 * ref.sum(0)) < 2e-5
   # dropout in the epilogue: keep-rate, scaling, determinism, and the same mask as mmt_cast16's dropout

@@ -69,6 +69,9 @@ if __name__ == "__main__":
     bench("dW1 wgrad split-K", 3072, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
     bench("dWqkv wgrad split-K", 1536, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
     bench("dWo wgrad split-K", 512, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
+  if which == "ffnup":
+    bench("FFN-up GELU (aux16+C16)", BS, 3072, 512, c16=1, epi=1, iters=3)
+    bench("QKV fwd (C16)", BS, 1536, 512, c16=1, iters=3)
   if which in ("all", "exp"):
     for K in (64, 256, 512, 1024, 2048):
       bench("N=3072 plain C16, K sweep", BS, 3072, K, c16=1)
