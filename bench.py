@@ -49,14 +49,14 @@ def hotpath_flops(w, B):
   """Algorithmic FLOPs of one train step (fwd + bwd = 3x fwd GEMM FLOPs), SURVEY.md §8(d)."""
   M, T, d, ff, L = len(w["modalities"]), w["T"], 512, 3072, 4
   S = 1 + M * (T + 1)
-  from oracle import mmt_oracle as O
-  ed = O.compute_dims(w["modalities"], w["face_dim"])
+  import workloads as W
+  ed = W.compute_dims(w["modalities"], w["face_dim"])
   sin = sum(v["dim"] for v in ed.values())
   lin = L * 2 * B * S * (4 * d * d + 2 * d * ff)
   attn = L * 4 * B * S * S * d
-  k1 = 2 * B * (T + 1) * sin * d
+  k1 = 2 * B * (T + 1) * sin * d          # ReduceDim: forward + weight gradient only (its inputs carry no gradient)
   k11 = M * 2 * B * (768 * d + d * d)
-  return 3.0 * (lin + attn + k1 + k11)
+  return 3.0 * (lin + attn + k11) + 2.0 * k1
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -112,11 +112,11 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ workloads
 def make_batches(w, B, n_batches, seed0, pin=False):
-  from oracle import mmt_oracle as O
-  ed = O.compute_dims(w["modalities"], w["face_dim"])
+  import workloads as W
+  ed = W.compute_dims(w["modalities"], w["face_dim"])
   out = []
   for i in range(n_batches):
-    b = O.synth_batch(ed, B, w["T"], seed=seed0 + i, dense=False)
+    b = W.synth_batch(ed, B, w["T"], seed=seed0 + i, dense=False)
     if pin:
       for k in ("features", "features_t", "features_ind", "features_avgpool", "features_maxpool"):
         for m in b[k]:
@@ -127,10 +127,27 @@ def make_batches(w, B, n_batches, seed0, pin=False):
   return ed, out
 
 
-def vb_params(w):
-  import mmt_test_helpers as H
-  return dict(H.VB_FULL, hidden_dropout_prob=DROPOUT, attention_probs_dropout_prob=DROPOUT,
+VB_FULL = {"vocab_size_or_config_json_file": 10, "hidden_size": 512, "num_hidden_layers": 4,
+           "num_attention_heads": 4, "intermediate_size": 3072, "hidden_act": "gelu",
+           "initializer_range": 0.02, "layer_norm_eps": 1e-12}     # configs_pub/eccv20/*.json vid_bert_params
+
+
+def vb_params(w, dropout=DROPOUT):
+  return dict(VB_FULL, hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout,
               max_position_embeddings=w["max_pos"], type_vocab_size=w["type_vocab"])
+
+
+def bench_config(w, world, precision):
+  """The benchmark definition -- IDENTICAL for both arms (the driver compares the two lines' `config`)."""
+  B = w["B"]
+  return {"workload": w["name"], "batch_per_gpu": B, "global_batch": B * world,
+          "scope": "hot path only: text encoder replaced by fixed [B,768] CLS features on both arms",
+          "step": "zero_grad+forward+MaxMarginRankingLoss+backward+Adam, dropout 0.1",
+          "parallelism": "dp%d: batch sharded over ranks, one all-gather of embeddings + gradient all-reduce" % world,
+          "l2": "GPU arm: ring of 4 distinct input batches (53.7 MB each at C2) and a >1 GB activation working set per "
+                "step, far above the 126 MB L2; no explicit flush",
+          "precision": "GPU arm: %s GEMM / attention operands, fp32 accumulation, statistics, residuals, master "
+                       "weights, gradients and loss; CPU arm: fp32" % precision}
 
 
 def batch_bytes(b):
@@ -162,7 +179,7 @@ def run_b200(args):
   from mmt_b200.model.loss import MaxMarginRankingLoss
   from mmt_b200.model.model import CENet
   from mmt_b200.optim import FusedAdam
-  from oracle import mmt_oracle as O
+  import workloads as W
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
@@ -171,6 +188,7 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
+    os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # lets NCCL collectives be captured in a CUDA graph
     dist.init_process_group("nccl", device_id=dev)
   _lib.load()
   torch.manual_seed(0)
@@ -180,20 +198,24 @@ def run_b200(args):
   vb = vb_params(w)
   NB = 4                                    # ring of distinct input batches: 4 x 53.5 MB > L2
   ed, batches = make_batches(w, B, NB, 1234 + 100 * rank, pin=True)
-  P = O.init_params(ed, vb, seed=0)
-  feed = TextFeed()
-  net = CENet(l2renorm=False, expert_dims=ed, tokenizer=None, keep_missing_modalities=True,
+  P = W.init_params(ed, vb, seed=0)
+  PREC = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16, "bf16": _lib.PREC_BF16}[args.precision]
+
+  def build_net(dropout, data_parallel):
+    f = TextFeed()
+    n = CENet(l2renorm=False, expert_dims=ed, tokenizer=None, keep_missing_modalities=True,
               test_caption_mode="indep", txt_inp="bertftn", txt_agg="bertftn", txt_wgh="emb",
               vid_wgh="none", vid_cont="bert", vid_inp="both", pos_enc="tint", out_tok="mxp",
-              vid_bert_params=vb, txt_pro="gbn",
-              txt_bert_params={"hidden_dropout_prob": DROPOUT,
-                               "attention_probs_dropout_prob": DROPOUT}, txt_bert=feed)
-  net.load_state_dict(P, strict=True)
-  net.to(dev).train()
-  net.cfg.precision = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16,
-                       "bf16": _lib.PREC_BF16}[args.precision]
-  if world > 1:
-    net.enable_data_parallel()
+              vid_bert_params=vb_params(w, dropout), txt_pro="gbn",
+              txt_bert_params={"hidden_dropout_prob": dropout, "attention_probs_dropout_prob": dropout}, txt_bert=f)
+    n.load_state_dict(P, strict=True)
+    n.to(dev).train()
+    n.cfg.precision = PREC
+    if data_parallel:
+      n.enable_data_parallel()
+    return n, f
+
+  net, feed = build_net(DROPOUT, world > 1)
   crit = MaxMarginRankingLoss(margin=0.05, fix_norm=True)
   opt = FusedAdam(net, lr=LR, weight_decay=WD)
 
@@ -214,7 +236,7 @@ def run_b200(args):
     out = net(**kw, out="conf", device=dev)
     loss = crit(out["cross_view_conf_matrix"])
     loss.backward()
-    opt.step()
+    opt.step()           # `opt` is looked up at call time (the stock-Adam e2e arm swaps it)
     return loss
 
   def barrier():
@@ -342,7 +364,19 @@ def run_b200(args):
   ms_e2e = timed(lambda i: e2e_step(i + 2), args.steps)
   e2e_eager = B * world * args.steps / (ms_e2e / 1e3)
   e2e_value, e2e_api = e2e_eager, "CENet.forward + MaxMarginRankingLoss + backward + FusedAdam.step, eager launches"
-  if world == 1 and not args.no_graph_e2e:
+  # the optimizer the UNCHANGED reference train.py:95-100 constructs: torch.optim.Adam over the module's parameters
+  # (views of the flat buffer).  Same host-buffer protocol, a few steps.
+  e2e_torch_adam = None
+  if world == 1 and not args.no_torch_adam:
+    opt_fused = opt
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=LR, weight_decay=WD)
+    for i in range(2):
+      e2e_step(i)
+    n_ta = max(4, args.steps // 2)
+    ms_ta = timed(lambda i: e2e_step(i + 2), n_ta)
+    e2e_torch_adam = B * n_ta / (ms_ta / 1e3)
+    opt = opt_fused
+  if not args.no_graph_e2e and (world == 1 or args.graph_dp):
     # Same host-buffer protocol through mmt_b200.graph.GraphedTrainStep (the repo's train-step API:
     # the same module / loss / optimizer objects captured once, replayed as one CUDA graph).  With a
     # loss read-back every step the host cannot run ahead, so the ~150 eager launches of a step are
@@ -375,23 +409,27 @@ def run_b200(args):
       "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "f16": "f16", "bf16": "bf16"}[args.precision],
       "data": "synthetic",
-      "config": {"workload": w["name"], "batch_per_gpu": B, "global_batch": B * world,
-                 "scope": "hot path only: text encoder replaced by fixed [B,768] CLS features on both arms",
-                 "step": "zero_grad+forward+MaxMarginRankingLoss+backward+Adam, dropout 0.1",
-                 "parallelism": "dp%d: all-gather of embeddings + one flat-gradient all-reduce" % world,
-                 "l2": "ring of %d distinct input batches (%.1f MB each) and a >2 GB activation working set per step; no explicit flush" % (NB, batch_bytes(batches[0]) / 1e6),
-                 "gemm_precision": args.precision,
-                 "launch": ("value: whole step replayed as one CUDA graph (%d kernels per step); "
-                            "e2e: eager launches through CENet.forward" % launches_per_step)
-                 if graphed is not None else "eager launches"},
+      "config": bench_config(w, world, args.precision),
+      "launch": ("value: whole step replayed as one CUDA graph (%d kernels per step); "
+                 "e2e: see e2e.api" % launches_per_step) if graphed is not None else "value: eager launches",
       "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
               "h2d_bytes_per_step": batch_bytes(batches[0]) * world, "d2h_bytes_per_step": 4 * world,
-              "api": e2e_api, "eager_value": e2e_eager},
+              "api": e2e_api, "eager_value": e2e_eager,
+              "eager_torch_adam_value": e2e_torch_adam,
+              "note": "value = best public train-step API; eager_value = the CENet.forward path the unchanged reference "
+                      "trainer runs with mmt_b200.optim.FusedAdam; eager_torch_adam_value = the same with the stock "
+                      "torch.optim.Adam that train.py:95-100 builds"},
       "gpu_launches": launches, "clocks": clk,
       "algorithmic_tflops_per_step": hotpath_flops(w, B) / 1e12,
       "achieved_tflops": hotpath_flops(w, B) * world / (ms / args.steps / 1e3) / 1e12,
   }
 
+  # ---- parity of THIS configuration (dropout off, fresh copies of the initial weights), outside every timed region
+  if not args.no_parity_check:
+    res["parity_check"] = parity_check(args, w, B, world, rank, dev, build_net, batches, P, crit)
+  prof = profile_facts()
+  if prof:
+    res["attn_tensor_pipe_pct"] = prof.get("attn_tensor_pipe_pct")
   if rank == 0:
     res["roofline"] = roofline_ffn(net, w, B, dev, args)
     if not args.no_hbm_probe:
@@ -403,6 +441,80 @@ def run_b200(args):
     print(json.dumps(res))
   if world > 1:
     dist.destroy_process_group()
+
+
+def profile_facts():
+  """Figures that only a profiler can give (tensor-pipe %, DRAM bytes), read from the committed ncu extract of THIS
+  round's build -- never measured inside bench.py (a number taken under a profiler is not a bench value)."""
+  p = os.path.join(ROOT, "profiles", "r02_kernels.json")
+  if os.path.isfile(p):
+    try:
+      return json.load(open(p))
+    except Exception:
+      return None
+  return None
+
+
+def parity_check(args, w, B, world, rank, dev, build_net, batches, P, crit):
+  """N = 1: one dropout-free train step of the benchmark configuration against the oracle port (conf, loss, every
+  gradient).  N > 1: the data-parallel step (rank-local batches) against a single-device step of the GLOBAL batch on
+  rank 0 -- so the scaling runs carry the data-parallel path's correctness."""
+  import torch.distributed as dist
+  import mmt_test_helpers as H
+  import workloads as W
+
+  def to_kw(b):
+    kw = H.batch_kwargs(b, dev)
+    return kw
+
+  out = {"dropout": 0.0, "batch_per_gpu": B}
+  net0, feed0 = build_net(0.0, world > 1)
+  feed0.cls = batches[0]["text_feat"].to(dev)
+  conf = net0(**to_kw(batches[0]), out="conf", device=dev)["cross_view_conf_matrix"]
+  loss = crit(conf)
+  loss.backward()
+  torch.cuda.synchronize()
+  if world == 1:
+    from oracle import mmt_oracle as O         # the checker (CPU), not the thing measured
+    ed = W.compute_dims(w["modalities"], w["face_dim"])
+    cfg = {"expert_dims": ed, "vid_bert_params": vb_params(w, 0.0), "txt_dropout": 0.0, "test_caption_mode": "indep"}
+    torch.set_num_threads(min(16, usable_cpus()))
+    conf_ref, loss_ref, grads = H.oracle_step(P, batches[0], cfg)
+    g_max, g_l2, worst, worst_l2 = H.grad_errors(net0, grads)
+    out.update({"against": "oracle port (fp32, CPU) on the same batch and weights",
+                "conf_max_rel": H.rel_err(conf, conf_ref), "conf_rel_l2": H.rel_l2(conf, conf_ref),
+                "loss_rel": abs(float(loss) - loss_ref) / abs(loss_ref),
+                "grad_max_rel": g_max, "grad_rel_l2": g_l2, "worst_tensor": [worst[0], worst[1]]})
+    out["pass"] = bool(out["conf_max_rel"] < 1e-3 and out["conf_rel_l2"] < 1e-3 and out["loss_rel"] < 1e-3 and
+                       g_max < 1e-3 and g_l2 < 1e-3) if args.precision in ("f16", "tf32", "fp32") else None
+  else:
+    # every rank regenerates all ranks' first batches (seeds are a function of the rank) -> the global batch
+    from mmt_b200.parallel import head_segments
+    gb = {}
+    parts = [make_batches(w, B, 1, 1234 + 100 * r)[1][0] for r in range(world)]
+    for k in parts[0]:
+      if isinstance(parts[0][k], dict):
+        gb[k] = {m: torch.cat([p_[k][m] for p_ in parts], 0) for m in parts[0][k]}
+      else:
+        gb[k] = torch.cat([p_[k] for p_ in parts], 0)
+    if rank == 0:
+      net1, feed1 = build_net(0.0, False)
+      feed1.cls = gb["text_feat"].to(dev)
+      conf1 = net1(**to_kw(gb), out="conf", device=dev)["cross_view_conf_matrix"]
+      loss1 = crit(conf1)
+      loss1.backward()
+      torch.cuda.synchronize()
+      g0, g1 = net0._grad_flat(), net1._grad_flat()
+      out.update({"against": "single-device step of the global batch (%d) on rank 0" % (B * world),
+                  "conf_max_rel": H.rel_err(conf, conf1), "loss_rel": abs(float(loss) - float(loss1)) / abs(float(loss1)),
+                  "grad_max_rel": float((g0 - g1).abs().max() / g1.abs().max()),
+                  "grad_rel_l2": float((g0 - g1).norm() / g1.norm())})
+      out["pass"] = bool(out["conf_max_rel"] < 1e-4 and out["loss_rel"] < 1e-5 and out["grad_max_rel"] < 1e-3)
+      del net1
+    dist.barrier()
+  del net0
+  torch.cuda.empty_cache()
+  return out
 
 
 def measured_peaks():
@@ -461,14 +573,15 @@ def roofline_ffn(net, w, B, dev, args):
   hbm, bf16, src = measured_peaks()
   peak = bf16 / 2.0 if args.precision == "tf32" else bf16
   ach = flops / (ms / 1e3) / 1e12
-  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at C2 from the committed ncu capture
-  # (profiles/r01_gemm_pair_and_attention_ncu_raw.csv: 37.4 MB read + 282.6 MB written at kernel end; an
-  # earlier capture of the round had 86.9 + 284.8 MB); algorithmic 377.7 MB -- no re-reads either way
-  traffic = 320.0e6 if (args.precision == "tf32" and BS == 13952) else None
-  return {"kernel": "FFN-up GEMM+bias+erf-GELU %dx%dx%d (%s)" % (BS, ff, d, args.precision),
+  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture of this round's build
+  prof = profile_facts() or {}
+  traffic = (prof.get("ffn_up_gemm") or {}).get("dram_bytes") if (BS == 13952 and args.precision == "f16") else None
+  alg = BS * d * 2 + ff * d * 2 + (2 * BS * ff * 2 if is16 else 2 * BS * ff * 4)
+  return {"kernel": "FFN-up GEMM+bias+erf-GELU(+GELU') %dx%dx%d (%s operands)" % (BS, ff, d, args.precision),
           "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-          "traffic": traffic, "ms_per_launch": ms,
-          "peak_note": "%s; tf32 peak taken as half the measured dense bf16 rate" % src}
+          "traffic": traffic, "algorithmic_bytes": alg, "ms_per_launch": ms,
+          "peak_note": "%s dense bf16 burst rate (fp16 runs at the same rate; tf32 = half)" % src,
+          "traffic_source": "profiles/r02_kernels.json" if traffic else None}
 
 
 def roofline_maxmargin(dev):
@@ -490,9 +603,11 @@ def roofline_maxmargin(dev):
   ms = e0.elapsed_time(e1) / reps
   hbm, _, src = measured_peaks()
   ach = 4.0 * n * n / (ms / 1e3) / 1e9
-  # traffic: dram__bytes_read.sum + write of one launch (profiles/r01_maxmargin_fwd_ncu_raw.csv)
+  prof = profile_facts() or {}
+  traffic = (prof.get("max_margin_fwd") or {}).get("dram_bytes")
   return {"kernel": "max_margin forward N=16384", "bound": "hbm", "achieved": ach, "peak": hbm,
-          "unit": "GB/s", "frac": ach / hbm, "traffic": 1.0771e9, "ms_per_launch": ms, "peak_note": src}
+          "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "algorithmic_bytes": 4.0 * n * n,
+          "ms_per_launch": ms, "peak_note": src, "traffic_source": "profiles/r02_kernels.json" if traffic else None}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -500,15 +615,16 @@ def cpu_step_fn(w, B, seed=1234):
   """The reference's train step restated on CPU (oracle port): same op sequence as the reference
   modules (unfused GELU, materialised attention, Python token assembly is vectorised)."""
   from oracle import mmt_oracle as O
-  ed = O.compute_dims(w["modalities"], w["face_dim"])
+  import workloads as W
+  ed = W.compute_dims(w["modalities"], w["face_dim"])
   vb = vb_params(w)
-  P = O.init_params(ed, vb, seed=0)
+  P = W.init_params(ed, vb, seed=0)
   params = [v.requires_grad_(True) for k, v in P.items()
             if v.is_floating_point() and "running" not in k and "pooler" not in k]
   opt = torch.optim.Adam(params, lr=LR, weight_decay=WD)
   cfg = {"expert_dims": ed, "vid_bert_params": vb, "txt_dropout": DROPOUT,
          "test_caption_mode": "indep"}
-  batch = O.synth_batch(ed, B, w["T"], seed=seed)
+  batch = W.synth_batch(ed, B, w["T"], seed=seed)
 
   def step():
     opt.zero_grad()
@@ -606,9 +722,7 @@ def run_reference(args):
       "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": w["name"], "batch_per_step": B,
-                 "scope": "hot path only: text encoder replaced by fixed [B,768] CLS features on both arms",
-                 "step": "zero_grad+forward+MaxMarginRankingLoss+backward+Adam, dropout 0.1"},
+      "config": bench_config(w, args.gpus, args.precision),
       "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
@@ -632,7 +746,11 @@ def main():
                   help="replay the step as one CUDA graph for `value` (mmt_b200/graph.py); measured gain on "
                        "B200 is < 1 % because the step is GPU-bound, so eager launches are the default")
   ap.add_argument("--no-hbm-probe", action="store_true")
+  ap.add_argument("--no-parity-check", action="store_true", help="skip the dropout-free parity / data-parallel check")
+  ap.add_argument("--no-torch-adam", action="store_true", help="skip the stock torch.optim.Adam e2e arm")
   ap.add_argument("--trace", action="store_true", help="print a kernel-timeline summary of 3 steps (rank 0)")
+  ap.add_argument("--graph-dp", action="store_true",
+                  help="also capture the data-parallel step (NCCL inside the CUDA graph) for the e2e arm at N > 1")
   ap.add_argument("--no-graph-e2e", action="store_true",
                   help="e2e through eager CENet.forward only (skip the GraphedTrainStep arm)")
   args = ap.parse_args()

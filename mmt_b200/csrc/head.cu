@@ -411,6 +411,8 @@ __global__ void __launch_bounds__(256) max_margin_kernel(const float* __restrict
                                                          float* __restrict__ dx,
                                                          float* __restrict__ ws /* [0]=loss sum, [2..2+n) diag counts */) {
   __shared__ float red[8];
+  pdl_trigger();
+  pdl_wait();                                    // before the first global access (the diagonal loads below)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = 4 * (blockIdx.x * 256 + threadIdx.x);
   const bool vec = (n % 4 == 0);
@@ -422,8 +424,6 @@ __global__ void __launch_bounds__(256) max_margin_kernel(const float* __restrict
   const int i_end = min(n, i_begin + rows_per_block);
   constexpr int RU = 4;                          // rows in flight per thread (memory-level parallelism)
   for (int ib = i_begin; ib < i_end; ib += RU) {
-  pdl_trigger();
-  pdl_wait();
     float dii[RU];
     float4 xr[RU];
 #pragma unroll

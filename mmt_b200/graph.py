@@ -20,9 +20,9 @@ class GraphedTrainStep:
   """
 
   def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3):
-    if getattr(net, "_dp", False):
-      raise NotImplementedError("GraphedTrainStep: capturing the data-parallel step (NCCL collectives inside "
-                                "the graph) is not supported yet; use the eager step with enable_data_parallel()")
+    # Data-parallel steps capture too: the all-gather and the gradient all-reduces become NCCL kernel nodes of the
+    # graph (torch's documented whole-network capture; needs TORCH_NCCL_ASYNC_ERROR_HANDLING=0 set before
+    # init_process_group, which bench.py does).  Every rank must capture and replay in lock-step.
     self.net, self.crit, self.opt = net, crit, opt
     self.kw, self.text = kwargs, text
     dev = net.flat.device

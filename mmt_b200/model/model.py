@@ -33,14 +33,25 @@ _SUPPORTED = dict(vid_cont="bert", vid_inp="both", pos_enc="tint", out_tok="mxp"
 
 
 def _build_txt_bert(txt_bert_params):
-  """bert-base-cased text encoder (third-party, outside the named hot path).
-  Uses local pretrained weights when they exist, else a random-init model of the same geometry
-  (vocab 28996 is what the reference hard-codes, model.py:205)."""
+  """bert-base-cased text encoder (third-party, outside the named hot path), built exactly as the
+  reference does (model.py:161: `TxtBertModel.from_pretrained('bert-base-cased', **txt_bert_params)`): a missing
+  or corrupt checkpoint FAILS.  Only with MMT_ALLOW_RANDOM_TXT_BERT=1 (benches / tests on machines without the
+  weights) a random-init model of the same geometry is substituted, loudly (vocab 28996 is what the reference
+  hard-codes, model.py:205)."""
+  import os
+  import warnings
   from transformers import BertConfig, BertModel
   kw = dict(txt_bert_params or {})
   try:
-    return BertModel.from_pretrained("bert-base-cased", local_files_only=True, **kw)
-  except Exception:   # no cached weights offline
+    return BertModel.from_pretrained("bert-base-cased", **kw)
+  except Exception as e:
+    if os.environ.get("MMT_ALLOW_RANDOM_TXT_BERT", "0") != "1":
+      raise RuntimeError("mmt_b200.CENet: could not load the pretrained 'bert-base-cased' text encoder (%s). "
+                         "Training / evaluating on random text-encoder weights is never done silently; set "
+                         "MMT_ALLOW_RANDOM_TXT_BERT=1 to allow a random-init model of the same geometry, or pass "
+                         "txt_bert=<module>." % (e,)) from e
+    warnings.warn("mmt_b200.CENet: 'bert-base-cased' weights unavailable; using a RANDOM-INIT text encoder "
+                  "(MMT_ALLOW_RANDOM_TXT_BERT=1)")
     return BertModel(BertConfig(vocab_size=28996, **kw))
 
 
@@ -309,6 +320,14 @@ class CENet(nn.Module):
       raise RuntimeError("enable_data_parallel needs an initialised torch.distributed group")
     self.dp_group = group
     self._dp = dist.get_world_size(group) > 1
+
+  def allreduce_outside_grads(self, group=None):
+    """Data-parallel step: all-reduce (SUM) the gradients of the trainable parameters that do not live in the flat
+    buffer -- the text encoder -- as ONE flattened NCCL call.  The loss is the global-batch mean and each rank
+    back-propagated only its own rows of d loss / d text, so the sum is the single-device gradient."""
+    from ..parallel import allreduce_grads
+    hot = set(id(p) for p in self._hot_params())
+    allreduce_grads([p for p in self.parameters() if id(p) not in hot], group)
 
   def _grad_flat(self):
     if self._gflat is None or self._gflat.device != self.flat.device:

@@ -30,6 +30,20 @@ def _all_gather_rows(x, group):
   return out
 
 
+def allreduce_grads(params, group=None):
+  """All-reduce (SUM) the .grad of `params` as ONE flattened collective (parameters outside the flat buffer)."""
+  grads = [p.grad for p in params if p.requires_grad and p.grad is not None]
+  if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return
+  flat = torch.cat([g.reshape(-1) for g in grads])
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  off = 0
+  for g in grads:
+    n = g.numel()
+    g.copy_(flat[off:off + n].view_as(g))
+    off += n
+
+
 def head_segments(layout):
   """[(offset, numel)] contiguous runs of the flat buffer that belong to the text head."""
   runs = []
@@ -117,4 +131,9 @@ class DPEncodeFn(torch.autograd.Function):
     net._publish_grads(gflat, accumulate)
     ctx.sv = None
     dtext = dtext_g[rank * rl:(rank + 1) * rl] if dtext_g is not None else None
+    if dtext is not None:
+      # every trainable parameter OUTSIDE the flat buffer (the text encoder: `txt_agg=bertftn` trains it) receives
+      # a per-rank partial gradient from this rank's slice of d loss / d text: sum them over the group once the
+      # whole backward pass has run (the same end-of-backward callback torch's DistributedDataParallel uses)
+      torch.autograd.Variable._execution_engine.queue_callback(lambda: net.allreduce_outside_grads(group))
     return None, dtext, None, None, None, None, None, None, None, None

@@ -39,7 +39,24 @@ def make_case(modalities, B, T, layers=4, dropout=0.0, caps=1, seed=1234, dense=
   return ed, vb, P, batch, cfg
 
 
-def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda", precision="fp32"):
+class TxtEmb(torch.nn.Module):
+  """A tiny TRAINABLE stand-in for the text encoder: hidden states = an embedding of the token ids (CLS row =
+  the embedding of the first token).  Exercises the gradient path into parameters outside the flat buffer."""
+
+  def __init__(self, vocab=64, dim=768, seed=5):
+    super().__init__()
+    g = torch.Generator().manual_seed(seed)
+    self.emb = torch.nn.Embedding(vocab, dim)
+    with torch.no_grad():
+      self.emb.weight.copy_(torch.randn(vocab, dim, generator=g))
+    self.config = types.SimpleNamespace(hidden_size=dim)
+    self.vocab = vocab
+
+  def forward(self, input_ids, **kw):
+    return (self.emb(input_ids % self.vocab),)
+
+
+def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda", precision="fp32", txt_bert=None):
   from mmt_b200 import _lib
   from mmt_b200.model.model import CENet
   W = batch["token_ids"].shape[2]
@@ -52,8 +69,8 @@ def build_cuda_net(ed, vb, P, batch, dropout=0.0, device="cuda", precision="fp32
               vid_bert_params=vb, txt_pro="gbn",
               txt_bert_params={"hidden_dropout_prob": dropout,
                                "attention_probs_dropout_prob": dropout},
-              txt_bert=TxtStub(hidden.to(device)))
-  net.load_state_dict(P, strict=True)
+              txt_bert=txt_bert if txt_bert is not None else TxtStub(hidden.to(device)))
+  net.load_state_dict(P, strict=txt_bert is None)
   net.cfg.precision = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "f16": _lib.PREC_F16,
                        "bf16": _lib.PREC_BF16}[precision]
   return net.to(device)

@@ -11,7 +11,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, precision="fp32", trainable_text=False):
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                     WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,7 +28,10 @@ def _worker(rank, world, port, q):
   ed, vb, P, batch, cfg = H.make_case(["s3d", "vggish", "ocr"], Bg, 9, layers=2)
   crit = MaxMarginRankingLoss(0.05, True)
   # single-device reference at the global batch
-  ref = H.build_cuda_net(ed, vb, P, batch, device=dev).train()
+  def txt():
+    return H.TxtEmb() if trainable_text else None
+
+  ref = H.build_cuda_net(ed, vb, P, batch, device=dev, precision=precision, txt_bert=txt()).train()
   conf_ref = ref(**H.batch_kwargs(batch, dev))["cross_view_conf_matrix"]
   loss_ref = crit(conf_ref)
   loss_ref.backward()
@@ -37,7 +40,7 @@ def _worker(rank, world, port, q):
   sl = slice(rank * bl, (rank + 1) * bl)
   local = {k: ({m: v[sl] for m, v in batch[k].items()} if isinstance(batch[k], dict) else batch[k][sl])
            for k in batch}
-  net = H.build_cuda_net(ed, vb, P, local, device=dev).train()
+  net = H.build_cuda_net(ed, vb, P, local, device=dev, precision=precision, txt_bert=txt()).train()
   net.enable_data_parallel()
   conf = net(**H.batch_kwargs(local, dev))["cross_view_conf_matrix"]
   loss = crit(conf)
@@ -53,11 +56,15 @@ def _worker(rank, world, port, q):
     worst = max(worst, float((g - gr).abs().max()) / max(float(gr.abs().max()), 1e-3 * gmax))
   errs["grad"] = worst
   errs["bn"] = H.rel_err(net.buf_flat, ref.buf_flat)
+  errs["txt_grad"] = 0.0
+  if trainable_text:      # parameters outside the flat buffer: per-rank partial gradients must have been summed
+    errs["txt_grad"] = H.rel_err(net.txt_bert.emb.weight.grad, ref.txt_bert.emb.weight.grad)
   q.put((rank, errs))
   dist.destroy_process_group()
 
 
-def test_two_gpu_data_parallel_matches_single_device_global_batch():
+@pytest.mark.parametrize("precision,trainable_text", [("fp32", False), ("f16", False), ("f16", True)])
+def test_two_gpu_data_parallel_matches_single_device_global_batch(precision, trainable_text):
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
   import torch.multiprocessing as mp
@@ -67,11 +74,12 @@ def test_two_gpu_data_parallel_matches_single_device_global_batch():
   s.close()
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
-  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q, precision, trainable_text)) for r in range(2)]
   for p in procs:
     p.start()
   res = [q.get(timeout=300) for _ in range(2)]
   for p in procs:
     p.join(timeout=60)
+  print("2-GPU data parallel vs single device (%s, trainable text %s): %s" % (precision, trainable_text, res))
   for rank, e in res:
-    assert e["conf"] < 1e-5 and e["loss"] < 1e-6 and e["grad"] < 2e-4 and e["bn"] < 1e-5, (rank, e)
+    assert e["conf"] < 1e-5 and e["loss"] < 1e-6 and e["grad"] < 2e-4 and e["bn"] < 1e-5 and e["txt_grad"] < 1e-5, (rank, e)

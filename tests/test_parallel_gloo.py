@@ -104,11 +104,16 @@ def _worker(rank, port, q):
   t_all = torch.randn(WORLD * B_LOCAL, TD, generator=g)
   gflat = torch.zeros_like(flat)
   published = {}
+  # a trainable "text encoder" OUTSIDE the flat buffer: its gradient is a per-rank partial sum that the
+  # end-of-backward callback must all-reduce (every published config trains txt_bert)
+  wenc = (torch.eye(TD) + 0.1 * torch.randn(TD, TD, generator=g)).requires_grad_(True)
   net = types.SimpleNamespace(
       cfg=None, flat=flat, buf_flat=None, layout=L, _hot_params=lambda: [],
-      _grad_flat=lambda: gflat, _publish_grads=lambda gf, acc: published.update(g=gf.clone()))
+      _grad_flat=lambda: gflat, _publish_grads=lambda gf, acc: published.update(g=gf.clone()),
+      allreduce_outside_grads=lambda group: parallel.allreduce_grads([wenc], group))
   sl = slice(rank * B_LOCAL, (rank + 1) * B_LOCAL)
-  text = t_all[sl].clone().requires_grad_(True)
+  raw = t_all[sl].clone().requires_grad_(True)
+  text = raw @ wenc
   anchor = torch.zeros(1, requires_grad=True)
   vid, txt, tw = parallel.DPEncodeFn.apply(anchor, text, net, x_all[sl], None, None, None, True, 5,
                                            None)
@@ -118,11 +123,13 @@ def _worker(rank, port, q):
   # single-process reference on the full batch
   f = flat.clone().requires_grad_(True)
   tr = t_all.clone().requires_grad_(True)
-  txt_r, tw_r = _head(f, tr)
+  wr = wenc.detach().clone().requires_grad_(True)
+  txt_r, tw_r = _head(f, tr @ wr)
   loss_r = _loss(_video(f, x_all), txt_r, tw_r)
   loss_r.backward()
   ok = (torch.allclose(published["g"], f.grad, rtol=1e-5, atol=1e-6) and
-        torch.allclose(text.grad, tr.grad[sl], rtol=1e-5, atol=1e-6) and
+        torch.allclose(raw.grad, tr.grad[sl], rtol=1e-5, atol=1e-6) and
+        torch.allclose(wenc.grad, wr.grad, rtol=1e-5, atol=1e-6) and
         abs(float(loss) - float(loss_r)) < 1e-6)
   q.put((rank, bool(ok), float((published["g"] - f.grad).abs().max())))
   dist.destroy_process_group()
