@@ -371,6 +371,35 @@ int mmt_adam16_step(float* p, const float* g, float* m, float* v, void* p16, int
                     float beta2, float eps, float weight_decay, int32_t step, const uint64_t* step_ctr,
                     float grad_scale, int32_t dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Text encoder: the reference's `txt_bert` is transformers' BertModel (bert-base-cased
+ * geometry, model/model.py:150-193 construction / freezing, :350-387 call).  Its encoder layers have the
+ * video encoder's algebra and run on the same kernels (mmt_gemm16 with fused epilogues, mmt_ln16_*); the
+ * entry points below are the parts that differ: token-id embeddings and attention over W <= 128 tokens with
+ * dh = 64.
+ * ------------------------------------------------------------------------------------------- */
+/* h[r] = dropout(LayerNorm(word[ids[r]] + pos[r % W] + type0)), rows = R*W; writes fp32 h and 16-bit h16. */
+int mmt_txt_embed_ln_fwd(const int32_t* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                         const float* beta, int64_t rows, int32_t W, int32_t vocab, int32_t d, float eps, float p_drop,
+                         uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* h, void* h16, float* mean,
+                         float* rstd, int32_t dtype, void* stream);
+/* backward: ACCUMULATES (atomics) dword [vocab,d], dpos [.,d], dtype0 [d], dgamma, dbeta; table pointers may be NULL
+ * (frozen embeddings). */
+int mmt_txt_embed_ln_bwd(const float* dh, const int32_t* ids, const float* word, const float* pos, const float* type0,
+                         const float* mean, const float* rstd, const float* gamma, int64_t rows, int32_t W, int32_t vocab,
+                         int32_t d, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site, float* dword,
+                         float* dpos, float* dtype0, float* dgamma, float* dbeta, void* stream);
+/* ctx16 = dropout(softmax(Q K^T * scale + (1 - mask) * -10000)) V per (caption, head); qkv16 [R*W, 3*H*64]. */
+int mmt_txt_attention_fwd(const void* qkv16, const float* mask, int32_t R, int32_t H, int32_t W, int32_t dh, float scale,
+                          float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site, void* ctx16, int32_t dtype,
+                          void* stream);
+/* dqkv16 (Q | K | V blocks, in dctx16's scale16 domain) from qkv16 and dctx16; probabilities are recomputed. */
+int mmt_txt_attention_bwd(const void* qkv16, const void* dctx16, const float* mask, int32_t R, int32_t H, int32_t W,
+                          int32_t dh, float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
+                          void* dqkv16, int32_t dtype, void* stream);
+/* out[n] += scale * sum_r X16[r*ld + n]: bias gradients from a 16-bit gradient tensor. */
+int mmt_colsum16(const void* X16, int64_t rows, int32_t n, int64_t ld, float scale, float* out, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,14 @@ SIGNATURES = {
     "mmt_attention16_bwd": (c_i32, [c_p] * 5 + [c_i32] * 4 + [c_f, c_f, c_u64, c_p, c_u32, c_f] + [c_p] * 4 +
                             [c_i32, c_p]),
     "mmt_adam16_step": (c_i32, [c_p] * 5 + [c_i64] + [c_f] * 5 + [c_i32, c_p, c_f, c_i32, c_p]),
+    # ---- text encoder ----
+    "mmt_txt_embed_ln_fwd": (c_i32, [c_p] * 6 + [c_i64, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_p, c_u32] + [c_p] * 4 +
+                             [c_i32, c_p]),
+    "mmt_txt_embed_ln_bwd": (c_i32, [c_p] * 8 + [c_i64, c_i32, c_i32, c_i32, c_f, c_u64, c_p, c_u32] + [c_p] * 5 + [c_p]),
+    "mmt_txt_attention_fwd": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_p, c_u32, c_p, c_i32, c_p]),
+    "mmt_txt_attention_bwd": (c_i32, [c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_f, c_f, c_u64, c_p, c_u32, c_p, c_i32,
+                                      c_p]),
+    "mmt_colsum16": (c_i32, [c_p, c_i64, c_i32, c_i64, c_f, c_p, c_i32, c_p]),
 }
 
 _lib = None

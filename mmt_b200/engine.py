@@ -58,6 +58,14 @@ class Config:
     self.save_attention_probs = os.environ.get("MMT_SAVE_PROBS", "1") != "0"
 
 
+  def enc_spec(self):
+    """engine16.EncSpec of the video encoder (parameter names of reference model/bert.py)."""
+    from .engine16 import EncSpec
+    if self.__dict__.get("_enc_spec") is None:
+      self._enc_spec = EncSpec(self.layout, "vid_bert.encoder.layer.%d.", "layer_norm", self.d, self.ff, self.H, self.L,
+                               self.eps, SITE_LAYER)
+    return self._enc_spec
+
   @property
   def scale16(self):
     """Power-of-two factor carried by 16-bit gradient tensors (fp16 range); 1 for bf16."""

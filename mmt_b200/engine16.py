@@ -67,6 +67,155 @@ def _e16(shape, like, dt):
   return torch.empty(shape, device=like.device, dtype=_lib.torch_dtype(dt))
 
 
+class EncSpec:
+  """Static description of a post-LN BERT encoder stack (reference model/bert.py:136-256; the same algebra as
+  transformers' BertLayer) whose parameters live in a flat buffer: the video encoder and the text encoder."""
+
+  def __init__(self, layout, prefix, ln_name, d, ff, H, L, eps, site_base):
+    self.layout, self.prefix, self.ln = layout, prefix, ln_name
+    self.d, self.ff, self.H, self.L, self.eps, self.site_base = d, ff, H, L, eps, site_base
+    self.dh = d // H
+
+  def off(self, l, name):
+    return self.layout.off((self.prefix % l) + name)
+
+
+def layers_forward(E, flat, f16, dt, h, h16, mask, B, S, p_hid, p_att, seed, ctr):
+  """L encoder layers on 16-bit operands.  h (fp32 residual stream) / h16 (its 16-bit copy) [B*S, d]; mask [B*S]
+  (1 = attend).  Returns (h_last fp32, per-layer saved activations)."""
+  lib = _lib.load()
+  st = stream_ptr()
+  d, ff, H, dh = E.d, E.ff, E.H, E.dh
+  BS = B * S
+  scale = 1.0 / math.sqrt(dh)
+  layers = []
+  for l in range(E.L):
+    site = E.site_base + 4 * l
+    ls = Saved()
+    ls.h16 = h16
+    # K4: fused QKV projection -> 16-bit only (bert.py:137-143)
+    qkv16 = _e16((BS, 3 * d), flat, dt)
+    gemm16(dt, BS, 3 * d, d, h16, d, 0, f16, d, 0, b_off=E.off(l, "attention.self.query.weight"),
+           bias=flat, bias_off=E.off(l, "attention.self.query.bias"), C16=qkv16, c16_ld=3 * d)
+    # K5: fused attention (bert.py:147-170)
+    ctx16 = _e16((BS, d), flat, dt)
+    lse = None
+    if dh == 128:
+      lse = _empty((B, H, S), flat)
+      check(lib.mmt_attention16_fwd(ptr(qkv16), ptr(mask), B, H, S, dh, scale, p_att, seed, ctr, site, ptr(ctx16),
+                                    ptr(lse), dt, st), "mmt_attention16_fwd")
+    else:
+      check(lib.mmt_txt_attention_fwd(ptr(qkv16), ptr(mask), B, H, S, dh, scale, p_att, seed, ctr, site, ptr(ctx16), dt,
+                                      st), "mmt_txt_attention_fwd")
+    # K6: attention output dense + dropout + residual in the GEMM epilogue, then LayerNorm (bert.py:186-188)
+    z1 = _empty((BS, d), flat)
+    gemm16(dt, BS, d, d, ctx16, d, 0, f16, d, 0, b_off=E.off(l, "attention.output.dense.weight"),
+           bias=flat, bias_off=E.off(l, "attention.output.dense.bias"), p_drop=p_hid, seed=seed, seed_ctr=ctr,
+           site=site + 1, add=h, add_ld=d, C32=z1, c32_ld=d)
+    a = _empty((BS, d), flat)
+    a16 = _e16((BS, d), flat, dt)
+    ls.mean1, ls.rstd1 = _empty((BS,), flat), _empty((BS,), flat)
+    check(lib.mmt_ln16_fwd(ptr(z1), ptr(flat, E.off(l, "attention.output.%s.weight" % E.ln)),
+                           ptr(flat, E.off(l, "attention.output.%s.bias" % E.ln)), BS, d, E.eps, ptr(a), ptr(a16),
+                           ptr(ls.mean1), ptr(ls.rstd1), dt, st), "mmt_ln16_fwd")
+    # K7: FFN up + erf-GELU (bert.py:218-219, 53): f16 = activation, g16 = gelu'(pre-activation) for the backward
+    g16, fa16 = _e16((BS, ff), flat, dt), _e16((BS, ff), flat, dt)
+    gemm16(dt, BS, ff, d, a16, d, 0, f16, d, 0, b_off=E.off(l, "intermediate.dense.weight"),
+           bias=flat, bias_off=E.off(l, "intermediate.dense.bias"), epilogue=EPI_GELU, aux16=g16, aux_ld=ff,
+           C16=fa16, c16_ld=ff)
+    # K8: FFN down + dropout + residual, LayerNorm (bert.py:234-236)
+    z2 = _empty((BS, d), flat)
+    gemm16(dt, BS, d, ff, fa16, ff, 0, f16, ff, 0, b_off=E.off(l, "output.dense.weight"),
+           bias=flat, bias_off=E.off(l, "output.dense.bias"), p_drop=p_hid, seed=seed, seed_ctr=ctr,
+           site=site + 2, add=a, add_ld=d, C32=z2, c32_ld=d)
+    hn = _empty((BS, d), flat)
+    hn16 = _e16((BS, d), flat, dt) if l + 1 < E.L else None
+    ls.mean2, ls.rstd2 = _empty((BS,), flat), _empty((BS,), flat)
+    check(lib.mmt_ln16_fwd(ptr(z2), ptr(flat, E.off(l, "output.%s.weight" % E.ln)),
+                           ptr(flat, E.off(l, "output.%s.bias" % E.ln)), BS, d, E.eps, ptr(hn), ptr(hn16),
+                           ptr(ls.mean2), ptr(ls.rstd2), dt, st), "mmt_ln16_fwd")
+    ls.qkv16, ls.ctx16, ls.lse, ls.z1, ls.a16, ls.u16, ls.f16, ls.z2 = qkv16, ctx16, lse, z1, a16, g16, fa16, z2
+    layers.append(ls)
+    h, h16 = hn, hn16
+  return h, layers
+
+
+def layers_backward(E, flat, f16, gflat, dt, layers, mask, B, S, dh_, p_hid, p_att, seed, ctr, sg, ws, on_layer_done=None):
+  """Backward of layers_forward: parameter gradients into gflat (weights overwritten, small vectors accumulated),
+  returns d loss / d (encoder input) [B*S, d] fp32.  `ws`: any object that may carry the zeroed dq32 workspace."""
+  lib = _lib.load()
+  st = stream_ptr()
+  d, ff, H, dh = E.d, E.ff, E.H, E.dh
+  BS = B * S
+  scale = 1.0 / math.sqrt(dh)
+  inv = 1.0 / sg
+  dq32 = None
+  if dh == 128:
+    dq32 = ws.__dict__.get("_dq32")
+    if dq32 is None or dq32.numel() != BS * d or dq32.device != flat.device:
+      dq32 = torch.zeros((BS, d), device=flat.device, dtype=torch.float32)     # kept zeroed by the attention backward
+      ws._dq32 = dq32
+  for l in reversed(range(E.L)):
+    site = E.site_base + 4 * l
+    ls = layers[l]
+    # --- LN2 backward: dz2 (fp32, to the residual a), dt2 (16-bit, to the FFN-down GEMMs), bias gradient ---
+    dz2 = _empty((BS, d), flat)
+    dt2 = _e16((BS, d), flat, dt)
+    check(lib.mmt_ln16_bwd(ptr(dh_), None, ptr(ls.z2), ptr(ls.mean2), ptr(ls.rstd2),
+                           ptr(flat, E.off(l, "output.%s.weight" % E.ln)), BS, d, p_hid, seed, ctr, site + 2, ptr(dz2),
+                           ptr(dt2), sg, ptr(gflat, E.off(l, "output.%s.weight" % E.ln)),
+                           ptr(gflat, E.off(l, "output.%s.bias" % E.ln)), ptr(gflat, E.off(l, "output.dense.bias")), dt, st),
+          "mmt_ln16_bwd")
+    # FFN down: dW2 [d, ff] = dt2^T @ f ; du = (dt2 @ W2) * gelu'(u) (+ its column sums = FFN-up bias gradient)
+    gemm16(dt, d, ff, BS, dt2, d, 1, ls.f16, ff, 1, alpha=inv, split_k=True, C32=gflat,
+           c32_off=E.off(l, "output.dense.weight"), c32_ld=ff)
+    du = _e16((BS, ff), flat, dt)
+    gemm16(dt, BS, ff, d, dt2, d, 0, f16, ff, 1, b_off=E.off(l, "output.dense.weight"), epilogue=EPI_DGELU,
+           aux16=ls.u16, aux_ld=ff, C16=du, c16_ld=ff, colsum=gflat,
+           colsum_off=E.off(l, "intermediate.dense.bias"), colsum_scale=inv)
+    # FFN up: dW1 [ff, d] = du^T @ a ; da = du @ W1
+    gemm16(dt, ff, d, BS, du, ff, 1, ls.a16, d, 1, alpha=inv, split_k=True, C32=gflat,
+           c32_off=E.off(l, "intermediate.dense.weight"), c32_ld=d)
+    da = _empty((BS, d), flat)
+    gemm16(dt, BS, d, ff, du, ff, 0, f16, d, 1, b_off=E.off(l, "intermediate.dense.weight"), alpha=inv,
+           C32=da, c32_ld=d)
+    # --- LN1 backward on (da + dz2) ---
+    dz1 = _empty((BS, d), flat)
+    dt1 = _e16((BS, d), flat, dt)
+    check(lib.mmt_ln16_bwd(ptr(da), ptr(dz2), ptr(ls.z1), ptr(ls.mean1), ptr(ls.rstd1),
+                           ptr(flat, E.off(l, "attention.output.%s.weight" % E.ln)), BS, d, p_hid, seed, ctr, site + 1,
+                           ptr(dz1), ptr(dt1), sg, ptr(gflat, E.off(l, "attention.output.%s.weight" % E.ln)),
+                           ptr(gflat, E.off(l, "attention.output.%s.bias" % E.ln)),
+                           ptr(gflat, E.off(l, "attention.output.dense.bias")), dt, st), "mmt_ln16_bwd")
+    # attention output dense: dWo = dt1^T @ ctx ; dctx = dt1 @ Wo (16-bit, scale16 domain)
+    gemm16(dt, d, d, BS, dt1, d, 1, ls.ctx16, d, 1, alpha=inv, split_k=True, C32=gflat,
+           c32_off=E.off(l, "attention.output.dense.weight"), c32_ld=d)
+    dctx = _e16((BS, d), flat, dt)
+    gemm16(dt, BS, d, d, dt1, d, 0, f16, d, 1, b_off=E.off(l, "attention.output.dense.weight"),
+           C16=dctx, c16_ld=d)
+    # --- fused attention backward: dqkv16 (scale16 domain) and the QKV bias gradient ---
+    dqkv = _e16((BS, 3 * d), flat, dt)
+    if dh == 128:
+      delta = _empty((B, H, S), flat)
+      check(lib.mmt_attention16_bwd(ptr(ls.qkv16), ptr(ls.ctx16), ptr(dctx), ptr(ls.lse), ptr(mask), B, H, S, dh,
+                                    scale, p_att, seed, ctr, site, sg, ptr(dqkv), ptr(dq32), ptr(delta),
+                                    ptr(gflat, E.off(l, "attention.self.query.bias")), dt, st), "mmt_attention16_bwd")
+    else:
+      check(lib.mmt_txt_attention_bwd(ptr(ls.qkv16), ptr(dctx), ptr(mask), B, H, S, dh, scale, p_att, seed, ctr, site,
+                                      ptr(dqkv), dt, st), "mmt_txt_attention_bwd")
+      check(lib.mmt_colsum16(ptr(dqkv), BS, 3 * d, 3 * d, inv, ptr(gflat, E.off(l, "attention.self.query.bias")), dt, st),
+            "mmt_colsum16")
+    # QKV projection: dWqkv [3d, d] = dqkv^T @ h_in ; dh = dz1 + dqkv @ Wqkv
+    gemm16(dt, 3 * d, d, BS, dqkv, 3 * d, 1, ls.h16, d, 1, alpha=inv, split_k=True, C32=gflat,
+           c32_off=E.off(l, "attention.self.query.weight"), c32_ld=d)
+    dh_ = _empty((BS, d), flat)
+    gemm16(dt, BS, d, 3 * d, dqkv, 3 * d, 0, f16, d, 1, b_off=E.off(l, "attention.self.query.weight"), alpha=inv,
+           add=dz1, add_ld=d, C32=dh_, c32_ld=d)
+    if on_layer_done is not None:
+      on_layer_done(l)
+  return dh_
+
+
 def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
   """ReduceDim -> token assembly -> BertModel -> AGG read-out on 16-bit operands (engine.video_forward)."""
   L = cfg.layout
@@ -123,51 +272,7 @@ def video_forward(cfg, flat, feats, maxp, ft, ind, training, seed):
       ptr(sv.mean0), ptr(sv.rstd0), dt, st), "mmt_embed_ln16_fwd")
 
   # ---- encoder layers (bert.py:249-256) ----
-  scale = 1.0 / math.sqrt(dh)
-  sv.layers = []
-  for l in range(cfg.L):
-    p = "vid_bert.encoder.layer.%d." % l
-    ls = Saved()
-    ls.h16 = h16
-    # K4: fused QKV projection -> 16-bit only (bert.py:137-143)
-    qkv16 = _e16((BS, 3 * d), flat, dt)
-    gemm16(dt, BS, 3 * d, d, h16, d, 0, f16, d, 0, b_off=L.off(p + "attention.self.query.weight"),
-           bias=flat, bias_off=L.off(p + "attention.self.query.bias"), C16=qkv16, c16_ld=3 * d)
-    # K5: fused attention (bert.py:147-170)
-    ctx16 = _e16((BS, d), flat, dt)
-    lse = _empty((B, H, S), flat)
-    check(lib.mmt_attention16_fwd(ptr(qkv16), ptr(sv.mask), B, H, S, dh, scale, p_att, seed, ctr,
-                                  SITE_LAYER + 4 * l, ptr(ctx16), ptr(lse), dt, st), "mmt_attention16_fwd")
-    # K6: attention output dense + dropout + residual in the GEMM epilogue, then LayerNorm (bert.py:186-188)
-    z1 = _empty((BS, d), flat)
-    gemm16(dt, BS, d, d, ctx16, d, 0, f16, d, 0, b_off=L.off(p + "attention.output.dense.weight"),
-           bias=flat, bias_off=L.off(p + "attention.output.dense.bias"), p_drop=p_hid, seed=seed, seed_ctr=ctr,
-           site=SITE_LAYER + 4 * l + 1, add=h, add_ld=d, C32=z1, c32_ld=d)
-    a = _empty((BS, d), flat)
-    a16 = _e16((BS, d), flat, dt)
-    ls.mean1, ls.rstd1 = _empty((BS,), flat), _empty((BS,), flat)
-    check(lib.mmt_ln16_fwd(ptr(z1), ptr(flat, L.off(p + "attention.output.layer_norm.weight")),
-                           ptr(flat, L.off(p + "attention.output.layer_norm.bias")), BS, d, cfg.eps, ptr(a),
-                           ptr(a16), ptr(ls.mean1), ptr(ls.rstd1), dt, st), "mmt_ln16_fwd")
-    # K7: FFN up + erf-GELU (bert.py:218-219, 53): f16 = activation, u16 = gelu'(pre-activation) for the backward
-    u16, fa16 = _e16((BS, ff), flat, dt), _e16((BS, ff), flat, dt)
-    gemm16(dt, BS, ff, d, a16, d, 0, f16, d, 0, b_off=L.off(p + "intermediate.dense.weight"),
-           bias=flat, bias_off=L.off(p + "intermediate.dense.bias"), epilogue=EPI_GELU, aux16=u16, aux_ld=ff,
-           C16=fa16, c16_ld=ff)
-    # K8: FFN down + dropout + residual, LayerNorm (bert.py:234-236)
-    z2 = _empty((BS, d), flat)
-    gemm16(dt, BS, d, ff, fa16, ff, 0, f16, ff, 0, b_off=L.off(p + "output.dense.weight"),
-           bias=flat, bias_off=L.off(p + "output.dense.bias"), p_drop=p_hid, seed=seed, seed_ctr=ctr,
-           site=SITE_LAYER + 4 * l + 2, add=a, add_ld=d, C32=z2, c32_ld=d)
-    hn = _empty((BS, d), flat)
-    hn16 = _e16((BS, d), flat, dt) if l + 1 < cfg.L else None
-    ls.mean2, ls.rstd2 = _empty((BS,), flat), _empty((BS,), flat)
-    check(lib.mmt_ln16_fwd(ptr(z2), ptr(flat, L.off(p + "output.layer_norm.weight")),
-                           ptr(flat, L.off(p + "output.layer_norm.bias")), BS, d, cfg.eps, ptr(hn), ptr(hn16),
-                           ptr(ls.mean2), ptr(ls.rstd2), dt, st), "mmt_ln16_fwd")
-    ls.qkv16, ls.ctx16, ls.lse, ls.z1, ls.a16, ls.u16, ls.f16, ls.z2 = qkv16, ctx16, lse, z1, a16, u16, fa16, z2
-    sv.layers.append(ls)
-    h, h16 = hn, hn16
+  h, sv.layers = layers_forward(cfg.enc_spec(), flat, f16, dt, h, h16, sv.mask, B, S, p_hid, p_att, seed, ctr)
 
   # ---- K10: expert read-out + L2 norm (model.py:583-587, 621-623) ----
   vid = _empty((B, M, d), flat)
@@ -316,65 +421,8 @@ def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
   dh_ = _empty((BS, d), flat)
   check(lib.mmt_readout_norm_bwd(ptr(dvid), ptr(sv.vid), ptr(sv.vinv), B, S, M, T, d, ptr(dh_), st),
         "mmt_readout_norm_bwd")
-  dq32 = cfg.__dict__.get("_dq32")
-  if dq32 is None or dq32.numel() != BS * d or dq32.device != flat.device:
-    dq32 = torch.zeros((BS, d), device=flat.device, dtype=torch.float32)     # kept zeroed by the attention backward
-    cfg._dq32 = dq32
-  for l in reversed(range(cfg.L)):
-    p = "vid_bert.encoder.layer.%d." % l
-    ls = sv.layers[l]
-    # --- LN2 backward: dz2 (fp32, to the residual a), dt2 (16-bit, to the FFN-down GEMMs), bias gradient ---
-    dz2 = _empty((BS, d), flat)
-    dt2 = _e16((BS, d), flat, dt)
-    check(lib.mmt_ln16_bwd(ptr(dh_), None, ptr(ls.z2), ptr(ls.mean2), ptr(ls.rstd2),
-                           ptr(flat, L.off(p + "output.layer_norm.weight")), BS, d, p_hid, seed, ctr,
-                           SITE_LAYER + 4 * l + 2, ptr(dz2), ptr(dt2), sg,
-                           ptr(gflat, L.off(p + "output.layer_norm.weight")),
-                           ptr(gflat, L.off(p + "output.layer_norm.bias")),
-                           ptr(gflat, L.off(p + "output.dense.bias")), dt, st), "mmt_ln16_bwd")
-    # FFN down: dW2 [d, ff] = dt2^T @ f ; du = (dt2 @ W2) * gelu'(u) (+ its column sums = FFN-up bias gradient)
-    gemm16(dt, d, ff, BS, dt2, d, 1, ls.f16, ff, 1, alpha=inv, split_k=True, C32=gflat,
-           c32_off=L.off(p + "output.dense.weight"), c32_ld=ff)
-    du = _e16((BS, ff), flat, dt)
-    gemm16(dt, BS, ff, d, dt2, d, 0, f16, ff, 1, b_off=L.off(p + "output.dense.weight"), epilogue=EPI_DGELU,
-           aux16=ls.u16, aux_ld=ff, C16=du, c16_ld=ff, colsum=gflat,
-           colsum_off=L.off(p + "intermediate.dense.bias"), colsum_scale=inv)
-    # FFN up: dW1 [ff, d] = du^T @ a ; da = du @ W1
-    gemm16(dt, ff, d, BS, du, ff, 1, ls.a16, d, 1, alpha=inv, split_k=True, C32=gflat,
-           c32_off=L.off(p + "intermediate.dense.weight"), c32_ld=d)
-    da = _empty((BS, d), flat)
-    gemm16(dt, BS, d, ff, du, ff, 0, f16, d, 1, b_off=L.off(p + "intermediate.dense.weight"), alpha=inv,
-           C32=da, c32_ld=d)
-    # --- LN1 backward on (da + dz2) ---
-    dz1 = _empty((BS, d), flat)
-    dt1 = _e16((BS, d), flat, dt)
-    check(lib.mmt_ln16_bwd(ptr(da), ptr(dz2), ptr(ls.z1), ptr(ls.mean1), ptr(ls.rstd1),
-                           ptr(flat, L.off(p + "attention.output.layer_norm.weight")), BS, d, p_hid, seed, ctr,
-                           SITE_LAYER + 4 * l + 1, ptr(dz1), ptr(dt1), sg,
-                           ptr(gflat, L.off(p + "attention.output.layer_norm.weight")),
-                           ptr(gflat, L.off(p + "attention.output.layer_norm.bias")),
-                           ptr(gflat, L.off(p + "attention.output.dense.bias")), dt, st), "mmt_ln16_bwd")
-    # attention output dense: dWo = dt1^T @ ctx ; dctx = dt1 @ Wo (16-bit, scale16 domain)
-    gemm16(dt, d, d, BS, dt1, d, 1, ls.ctx16, d, 1, alpha=inv, split_k=True, C32=gflat,
-           c32_off=L.off(p + "attention.output.dense.weight"), c32_ld=d)
-    dctx = _e16((BS, d), flat, dt)
-    gemm16(dt, BS, d, d, dt1, d, 0, f16, d, 1, b_off=L.off(p + "attention.output.dense.weight"),
-           C16=dctx, c16_ld=d)
-    # --- fused attention backward: dqkv16 (scale16 domain) and the QKV bias gradient ---
-    dqkv = _e16((BS, 3 * d), flat, dt)
-    delta = _empty((B, H, S), flat)
-    check(lib.mmt_attention16_bwd(ptr(ls.qkv16), ptr(ls.ctx16), ptr(dctx), ptr(ls.lse), ptr(sv.mask), B, H, S, dh,
-                                  scale, p_att, seed, ctr, SITE_LAYER + 4 * l, sg, ptr(dqkv), ptr(dq32), ptr(delta),
-                                  ptr(gflat, L.off(p + "attention.self.query.bias")), dt, st),
-          "mmt_attention16_bwd")
-    # QKV projection: dWqkv [3d, d] = dqkv^T @ h_in ; dh = dz1 + dqkv @ Wqkv
-    gemm16(dt, 3 * d, d, BS, dqkv, 3 * d, 1, ls.h16, d, 1, alpha=inv, split_k=True, C32=gflat,
-           c32_off=L.off(p + "attention.self.query.weight"), c32_ld=d)
-    dh_ = _empty((BS, d), flat)
-    gemm16(dt, BS, d, 3 * d, dqkv, 3 * d, 0, f16, d, 1, b_off=L.off(p + "attention.self.query.weight"), alpha=inv,
-           add=dz1, add_ld=d, C32=dh_, c32_ld=d)
-    if on_layer_done is not None:
-      on_layer_done(l)
+  dh_ = layers_backward(cfg.enc_spec(), flat, f16, gflat, dt, sv.layers, sv.mask, B, S, dh_, p_hid, p_att, seed, ctr,
+                        sg, cfg, on_layer_done)
 
   # --- embeddings + token assembly backward ---
   R1 = B * (T + 1)

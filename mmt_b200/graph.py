@@ -20,9 +20,13 @@ class GraphedTrainStep:
   """
 
   def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3):
-    # Data-parallel steps capture too: the all-gather and the gradient all-reduces become NCCL kernel nodes of the
-    # graph (torch's documented whole-network capture; needs TORCH_NCCL_ASYNC_ERROR_HANDLING=0 set before
-    # init_process_group, which bench.py does).  Every rank must capture and replay in lock-step.
+    import os
+    if getattr(net, "_dp", False) and os.environ.get("MMT_GRAPH_DP", "0") != "1":
+      # Capturing the data-parallel step (NCCL all-gather / all-reduce nodes inside the graph) is EXPERIMENTAL: the
+      # first attempt on 2 B200s (torch 2.11, NCCL 2.28, TORCH_NCCL_ASYNC_ERROR_HANDLING=0) never finished its
+      # capture.  Opt in with MMT_GRAPH_DP=1; the supported data-parallel path is the eager step.
+      raise NotImplementedError("GraphedTrainStep: the data-parallel step is not captured (set MMT_GRAPH_DP=1 to try); "
+                                "use the eager step with enable_data_parallel()")
     self.net, self.crit, self.opt = net, crit, opt
     self.kw, self.text = kwargs, text
     dev = net.flat.device
@@ -56,6 +60,8 @@ class GraphedTrainStep:
     opt.step_ctr); the fp32 / tf32 entry points read the library-wide pointer."""
     if _lib.is16(self.net.cfg.precision):
       self.net.cfg.seed_ctr = _lib.ptr(self.ctr)
+      if hasattr(getattr(self.net, "txt_bert", None), "seed_ctr"):
+        self.net.txt_bert.seed_ctr = _lib.ptr(self.ctr)
       if hasattr(self.opt, "step_ctr"):
         self.opt.step_ctr = _lib.ptr(self.ctr)
     else:
@@ -64,6 +70,8 @@ class GraphedTrainStep:
   def _detach(self):
     if _lib.is16(self.net.cfg.precision):
       self.net.cfg.seed_ctr = None
+      if hasattr(getattr(self.net, "txt_bert", None), "seed_ctr"):
+        self.net.txt_bert.seed_ctr = None
       if hasattr(self.opt, "step_ctr"):
         self.opt.step_ctr = None
     else:

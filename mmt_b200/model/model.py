@@ -162,7 +162,14 @@ class CENet(nn.Module):
     if txt_bert_params is None:
       dout = vid_bert_params["hidden_dropout_prob"]
       txt_bert_params = {"hidden_dropout_prob": dout, "attention_probs_dropout_prob": dout}
-    self.txt_bert = txt_bert if txt_bert is not None else _build_txt_bert(txt_bert_params)
+    if txt_bert is None:
+      txt_bert = _build_txt_bert(txt_bert_params)
+      import os
+      if os.environ.get("MMT_TXT_BERT", "native") == "native":
+        # the same weights on this repo's kernels (mmt_b200/model/txt_bert.py); MMT_TXT_BERT=hf keeps transformers' module
+        from .txt_bert import TxtBert
+        txt_bert = TxtBert.from_hf(txt_bert)
+    self.txt_bert = txt_bert
     if state == "frz":
       for name, param in self.txt_bert.named_parameters():
         parts = name.split(".")
@@ -321,12 +328,24 @@ class CENet(nn.Module):
     self.dp_group = group
     self._dp = dist.get_world_size(group) > 1
 
+  @property
+  def w16(self):
+    """The 16-bit weight copy of the hot-path parameters (None in the fp32 / tf32 modes)."""
+    return self.cfg.w16 if _lib.is16(self.cfg.precision) else None
+
   def allreduce_outside_grads(self, group=None):
     """Data-parallel step: all-reduce (SUM) the gradients of the trainable parameters that do not live in the flat
     buffer -- the text encoder -- as ONE flattened NCCL call.  The loss is the global-batch mean and each rank
     back-propagated only its own rows of d loss / d text, so the sum is the single-device gradient."""
+    import torch.distributed as dist
     from ..parallel import allreduce_grads
     hot = set(id(p) for p in self._hot_params())
+    tb = self.txt_bert
+    if hasattr(tb, "_gflat") and tb._gflat is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+      # a flat-buffer text encoder (TxtBert): its parameters' gradients are views of ONE buffer -> one in-place call
+      if any(p.grad is not None for p in tb._hot_params()):
+        dist.all_reduce(tb._gflat, op=dist.ReduceOp.SUM, group=group)
+      hot |= set(id(p) for p in tb._hot_params())
     allreduce_grads([p for p in self.parameters() if id(p) not in hot], group)
 
   def _grad_flat(self):

@@ -27,6 +27,12 @@ class FusedAdam:
     self.m = torch.zeros_like(net.flat)
     self.v = torch.zeros_like(net.flat)
     hot = set(id(p) for p in net._hot_params())
+    # a text encoder that also lives in a flat buffer (mmt_b200.model.txt_bert.TxtBert) gets its own fused instance
+    self.sub = []
+    tb = getattr(net, "txt_bert", None)
+    if tb is not None and hasattr(tb, "flat") and hasattr(tb, "_hot_params") and any(p.requires_grad for p in tb._hot_params()):
+      self.sub.append(FusedAdam(tb, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale))
+      hot |= set(id(p) for p in tb._hot_params())
     others = [p for p in net.parameters() if id(p) not in hot and p.requires_grad]
     self.other = torch.optim.Adam(others, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay) \
         if others else None
@@ -51,7 +57,7 @@ class FusedAdam:
     L = self.net.layout
     for name, seg in L.segments.items():
       p = self.net._param(name)
-      if not p.requires_grad or name.startswith("vid_bert.pooler."):
+      if not p.requires_grad or name.startswith(("vid_bert.pooler.", "pooler.")):
         continue
       lo, hi = seg.offset, seg.offset + (seg.numel + 3) // 4 * 4
       if runs and runs[-1][1] >= lo:
@@ -63,6 +69,8 @@ class FusedAdam:
     return runs
 
   def zero_grad(self, set_to_none=True):
+    for sub in self.sub:
+      sub.zero_grad(set_to_none)
     for p in self.net._hot_params():
       p.grad = None
     if self.other is not None:
@@ -71,7 +79,8 @@ class FusedAdam:
   def state_dict(self):
     return {"t": self.t, "m": self.m, "v": self.v, "param_groups": [{k: v for k, v in g.items() if k != "params"}
                                                                    for g in self.param_groups[:1]],
-            "other": self.other.state_dict() if self.other is not None else None}
+            "other": self.other.state_dict() if self.other is not None else None,
+            "sub": [s_.state_dict() for s_ in self.sub]}
 
   def load_state_dict(self, sd):
     self.t = int(sd["t"])
@@ -81,9 +90,15 @@ class FusedAdam:
       self.param_groups[0][k] = v
     if self.other is not None and sd.get("other") is not None:
       self.other.load_state_dict(sd["other"])
+    for s_, d_ in zip(self.sub, sd.get("sub", [])):
+      s_.load_state_dict(d_)
 
   def step(self):
     net = self.net
+    for sub in self.sub:
+      sub.param_groups[0].update({k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")})
+      sub.step_ctr = self.step_ctr
+      sub.step()
     if self.m.device != net.flat.device:
       self.m, self.v = self.m.to(net.flat.device), self.v.to(net.flat.device)
     if self._runs is None:
@@ -97,7 +112,7 @@ class FusedAdam:
     missing = []
     for i, p in enumerate(params):
       if p.grad is None:
-        if p.requires_grad and not net._names[i].startswith("vid_bert.pooler."):
+        if p.requires_grad and not net._names[i].startswith(("vid_bert.pooler.", "pooler.")):
           missing.append(i)
         continue
       fresh = True
@@ -123,7 +138,7 @@ class FusedAdam:
         runs = self._runs
       lib = _lib.load()
       st = _lib.stream_ptr()
-      w16 = net.cfg.w16 if _lib.is16(net.cfg.precision) else None
+      w16 = getattr(net, "w16", None)           # 16-bit weight copy of the module (None in the fp32 / tf32 modes)
       for lo, hi in runs:
         if w16 is not None:
           _lib.check(lib.mmt_adam16_step(_lib.ptr(net.flat, lo), _lib.ptr(g, lo), _lib.ptr(self.m, lo),
@@ -133,7 +148,7 @@ class FusedAdam:
           _lib.check(lib.mmt_adam_step(_lib.ptr(net.flat, lo), _lib.ptr(g, lo), _lib.ptr(self.m, lo),
                                        _lib.ptr(self.v, lo), hi - lo, lr, b1, b2, eps, wd, self.t,
                                        self.grad_scale, st), "mmt_adam_step")
-      if w16 is not None:
+      if w16 is not None and hasattr(net, "cfg"):
         w16.refresh_padded(net.cfg, net.flat)      # row-padded ReduceDim copies (two small casts)
     if self.other is not None:
       self.other.step()

@@ -172,11 +172,11 @@ def recorder(monkeypatch):
   return rec
 
 
-def _mini_net():
+def _mini_net(heads=4):
   import types
   from mmt_b200.model.model import CENet
   ed = O.compute_dims(["s3d", "vggish", "ocr"])
-  vb = {"hidden_size": 128, "num_hidden_layers": 2, "num_attention_heads": 4,
+  vb = {"hidden_size": 128, "num_hidden_layers": 2, "num_attention_heads": heads,
         "intermediate_size": 256, "hidden_act": "gelu", "hidden_dropout_prob": 0.1,
         "attention_probs_dropout_prob": 0.1, "max_position_embeddings": 32, "type_vocab_size": 19,
         "initializer_range": 0.02, "layer_norm_eps": 1e-12}
@@ -195,10 +195,12 @@ def _mini_net():
   return net, ed
 
 
-def test_engine16_dry_run_addresses_only_owned_memory(recorder):
+@pytest.mark.parametrize("heads", [1, 2])
+def test_engine16_dry_run_addresses_only_owned_memory(recorder, heads):
   """The 16-bit operand sequencing (engine16.py): every pointer / extent handed to the library lies inside a
-  tensor the host code allocated, TMA alignment rules hold for every GEMM operand."""
-  net, ed = _mini_net()
+  tensor the host code allocated, TMA alignment rules hold for every GEMM operand.  heads=1: dh = 128, the
+  tcgen05 attention kernels; heads=2: dh = 64, the short-sequence attention of the text encoder."""
+  net, ed = _mini_net(heads)
   net.cfg.precision = _lib.PREC_F16
   net._prepare16()
   B, T = 5, 7
@@ -221,7 +223,8 @@ def test_engine16_dry_run_addresses_only_owned_memory(recorder):
                        precision=_lib.PREC_F16, scale16=net.cfg.scale16)
   assert recorder.calls.count("mmt_gemm16") > 60
   for name in ("mmt_pack_inputs16", "mmt_embed_ln16_fwd", "mmt_embed_ln16_bwd", "mmt_ln16_fwd", "mmt_ln16_bwd",
-               "mmt_attention16_fwd", "mmt_attention16_bwd", "mmt_cast16", "mmt_readout_norm_fwd",
+               "mmt_attention16_fwd" if heads == 1 else "mmt_txt_attention_fwd",
+               "mmt_attention16_bwd" if heads == 1 else "mmt_txt_attention_bwd", "mmt_cast16", "mmt_readout_norm_fwd",
                "mmt_readout_norm_bwd", "mmt_geu_gate_fwd", "mmt_geu_gate_bwd", "mmt_moe_softmax_fwd",
                "mmt_moe_softmax_bwd", "mmt_sims_combine_fwd", "mmt_sims_combine_bwd", "mmt_colsum"):
     assert name in recorder.calls, name

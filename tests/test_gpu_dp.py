@@ -82,4 +82,4 @@ def test_two_gpu_data_parallel_matches_single_device_global_batch(precision, tra
     p.join(timeout=60)
   print("2-GPU data parallel vs single device (%s, trainable text %s): %s" % (precision, trainable_text, res))
   for rank, e in res:
-    assert e["conf"] < 1e-5 and e["loss"] < 1e-6 and e["grad"] < 2e-4 and e["bn"] < 1e-5 and e["txt_grad"] < 1e-5, (rank, e)
+    assert e["conf"] < 1e-5 and e["loss"] < 1e-6 and e["grad"] < 2e-4 and e["bn"] < 1e-5 and e["txt_grad"] < 1e-4, (rank, e)
