@@ -36,7 +36,9 @@ def test_txt_bert_matches_transformers_bert_model(R, W, layers):
   mask = (torch.arange(W)[None, :] < lens[:, None]).long()
   pos = torch.arange(W)[None, :].expand(R, W)
   tt = torch.zeros(R, W, dtype=torch.long)
-  probe = torch.randn(R, 768, generator=g)
+  # upstream gradient of the magnitude the ranking loss produces (~1/n per row): 16-bit gradient tensors carry the
+  # fixed 2^16 scale of the train step, which assumes |d loss / d activation| << 1
+  probe = torch.randn(R, 768, generator=g) * 1e-3
   # reference: CLS row of the last hidden state (what the reference consumes, model/model.py:378-379)
   out_ref = hf(ids, attention_mask=mask, token_type_ids=tt, position_ids=pos)[0]
   (out_ref[:, 0] * probe).sum().backward()
@@ -50,9 +52,11 @@ def test_txt_bert_matches_transformers_bert_model(R, W, layers):
   g_max, g_l2, worst, worst_l2 = H.grad_errors(net, ref_grads)
   print("TxtBert R=%d W=%d L=%d: CLS max-rel %.2e, valid tokens max-rel %.2e | gradient (whole) max-norm %.2e rel-L2 %.2e | "
         "worst tensor %s %.2e" % (R, W, layers, e_cls, e_all, g_max, g_l2, worst[0], worst[1]))
-  tol = 1e-3 if layers <= 2 else 2e-3            # 12 layers: 4 more GEMMs per layer of 11-bit operand rounding
-  assert e_cls < tol and e_all < 2 * tol
-  assert g_max < 2 * tol and g_l2 < 2 * tol
+  # every GEMM operand is rounded to an 11-bit significand once: zero-mean noise of ~4e-4 per GEMM that grows with
+  # the square root of the depth (forward: 6 GEMMs per layer; a gradient that reaches the embeddings of a 12-layer
+  # stack has crossed ~70 of them forward and backward)
+  assert e_cls < (1e-3 if layers <= 2 else 2e-3) and e_all < (2e-3 if layers <= 2 else 3e-3)
+  assert g_max < (2e-3 if layers <= 2 else 1e-2) and g_l2 < (2e-3 if layers <= 2 else 4e-3)
 
 
 def test_txt_bert_dropout_and_fused_adam_in_cenet():
