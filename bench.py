@@ -424,6 +424,11 @@ def run_b200(args):
       "achieved_tflops": hotpath_flops(w, B) * world / (ms / args.steps / 1e3) / 1e12,
   }
 
+  # ---- scope B: the FULL CENet train step, text encoder included (bert-base-cased geometry, random init: the
+  # pretrained weights cannot be fetched here), on this repo's kernels (mmt_b200/model/txt_bert.py) ----
+  if world == 1 and not args.no_scope_b and _lib.is16(PREC):
+    res["scope_b"] = scope_b(args, w, B, dev, P, ed, resident, crit, PREC)
+
   # ---- parity of THIS configuration (dropout off, fresh copies of the initial weights), outside every timed region
   if not args.no_parity_check:
     res["parity_check"] = parity_check(args, w, B, world, rank, dev, build_net, batches, P, crit)
@@ -441,6 +446,54 @@ def run_b200(args):
     print(json.dumps(res))
   if world > 1:
     dist.destroy_process_group()
+
+
+def scope_b(args, w, B, dev, P, ed, resident, crit, PREC):
+  """Full `CENet` step (SURVEY.md §8(d) scope B): token ids -> text encoder (12 x BERT-base layers, W = 30) -> CLS ->
+  text head, plus the whole video side, forward + backward + fused Adam over both flat parameter buffers."""
+  from mmt_b200.model.model import CENet
+  from mmt_b200.model.txt_bert import TxtBert
+  from mmt_b200.optim import FusedAdam
+  tb = TxtBert(hidden_dropout_prob=DROPOUT, attention_probs_dropout_prob=DROPOUT, precision=PREC)
+  net = CENet(l2renorm=False, expert_dims=ed, tokenizer=None, keep_missing_modalities=True,
+              test_caption_mode="indep", txt_inp="bertftn", txt_agg="bertftn", txt_wgh="emb",
+              vid_wgh="none", vid_cont="bert", vid_inp="both", pos_enc="tint", out_tok="mxp",
+              vid_bert_params=vb_params(w), txt_pro="gbn",
+              txt_bert_params={"hidden_dropout_prob": DROPOUT, "attention_probs_dropout_prob": DROPOUT}, txt_bert=tb)
+  net.load_state_dict(P, strict=False)
+  net.to(dev).train()
+  net.cfg.precision = PREC
+  opt = FusedAdam(net, lr=LR, weight_decay=WD)
+
+  def step(kw):
+    opt.zero_grad()
+    loss = crit(net(**kw, out="conf", device=dev)["cross_view_conf_matrix"])
+    loss.backward()
+    opt.step()
+    return loss
+
+  NB = len(resident)
+  for i in range(4):
+    step(resident[i % NB][0])
+  torch.cuda.synchronize()
+  n = max(4, args.steps // 2)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(n):
+    step(resident[i % NB][0])
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / n
+  Wt = resident[0][0]["token_ids"].shape[2]
+  txt_flops = 3.0 * 12 * 2 * B * Wt * (4 * 768 * 768 + 2 * 768 * 3072)
+  out = {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": n,
+         "text_encoder": "mmt_b200.model.txt_bert.TxtBert, BERT-base geometry (12L/768/12H, vocab 28996), W=%d, random init" % Wt,
+         "trainable_parameters": int(sum(p.numel() for p in net.parameters() if p.requires_grad)),
+         "algorithmic_tflops_per_step": (hotpath_flops(w, B) + txt_flops) / 1e12}
+  out["achieved_tflops"] = out["algorithmic_tflops_per_step"] / (ms / 1e3)
+  del net, opt, tb
+  torch.cuda.empty_cache()
+  return out
 
 
 def profile_facts():
@@ -746,6 +799,7 @@ def main():
                   help="replay the step as one CUDA graph for `value` (mmt_b200/graph.py); measured gain on "
                        "B200 is < 1 % because the step is GPU-bound, so eager launches are the default")
   ap.add_argument("--no-hbm-probe", action="store_true")
+  ap.add_argument("--no-scope-b", action="store_true", help="skip the full-CENet (text encoder included) measurement")
   ap.add_argument("--no-parity-check", action="store_true", help="skip the dropout-free parity / data-parallel check")
   ap.add_argument("--no-torch-adam", action="store_true", help="skip the stock torch.optim.Adam e2e arm")
   ap.add_argument("--trace", action="store_true", help="print a kernel-timeline summary of 3 steps (rank 0)")
