@@ -647,31 +647,47 @@ __global__ void __launch_bounds__(256) attn_delta16_kernel(const uint16_t* __res
   }
 }
 
-// dq32 [rows, d] -> the Q block of dqkv16 (16-bit, already in the scale16 domain), its bias-gradient column sums
-// (divided by scale16), and dq32 zeroed again for the next layer's accumulation.
-template <int VEC>
-__global__ void __launch_bounds__(WARPS * 32) attn_dq_finish_kernel(float* __restrict__ dq32, int64_t rows,
-                                                                    uint16_t* __restrict__ dqkv16, float* __restrict__ dbias,
-                                                                    float inv_scale16, int bf16) {
+// dq32 [rows, d] -> the Q block of dqkv16 (16-bit, already in the scale16 domain); dq32 is left zeroed for the next
+// layer's accumulation.  Pure streaming, one float4 per thread (the Q bias gradient is a separate mmt_colsum16-style
+// pass over the 16-bit result: a fused column sum put one atomic per block and column on 128 hot addresses).
+__global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict__ dq32, int64_t n4, int d4,
+                                                            uint16_t* __restrict__ dqkv16, int bf16) {
   pdl_trigger();
   pdl_wait();
-  constexpr int d = 128 * VEC;
-  __shared__ float4 red[WARPS * VEC * 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 acc[VEC], zero[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
-    float4 g[VEC];
-    load_row<VEC>(dq32 + r * d, lane, g);
-    store_row<VEC>(dq32 + r * d, lane, zero);
-    store_row16<VEC>(dqkv16 + r * 3 * d, lane, g, 1.0f, bf16 != 0);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i].x += g[i].x; acc[i].y += g[i].y; acc[i].z += g[i].z; acc[i].w += g[i].w; }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = dq32[i];
+    dq32[i] = zero;
+    const int64_t r = i / d4;
+    const int c4 = (int)(i - r * d4);
+    *reinterpret_cast<uint2*>(dqkv16 + r * 3 * (4 * (int64_t)d4) + 4 * c4) = pack4(g, bf16 != 0);
   }
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) F4_OP(acc[i], acc[i].x * inv_scale16, acc[i].y * inv_scale16, acc[i].z * inv_scale16, acc[i].w * inv_scale16);
-  flush_cols<VEC>(acc, dbias, lane, warp, red);
+}
+
+// out[n] += scale * sum_r X16[r*ld + n]   (bias gradient of the Q block)
+__global__ void __launch_bounds__(256) attn_colsum16_kernel(const uint16_t* __restrict__ X, int64_t rows, int n, int64_t ld,
+                                                            float scale, float* __restrict__ out, int bf16) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float4 red[8][32];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const int ty = threadIdx.y;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < n) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
+      const float4 v = unpack4(*reinterpret_cast<const uint2*>(X + r * ld + 4 * c4), bf16 != 0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[ty][threadIdx.x] = acc;
+  __syncthreads();
+  if (ty == 0 && c4 * 4 < n) {
+    for (int w = 1; w < 8; ++w) {
+      const float4 t = red[w][threadIdx.x];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomic_add4(out + 4 * c4, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+  }
 }
 }  // namespace bwd
 
@@ -789,10 +805,19 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);
   MMT_LAUNCH_CHECK("attention16_bwd_kernel");
   {
-    const int grid2 = row_grid(rows);
-    DISPATCH_VEC(d_model, (launch_pdl(bwd::attn_dq_finish_kernel<V>, dim3(grid2), dim3(WARPS * 32), 0, st, dq32, rows,
-                                      reinterpret_cast<uint16_t*>(dqkv16), dbias, 1.0f / scale16, bf16)));
+    const int64_t n4 = rows * (d_model / 4);
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+    launch_pdl(bwd::attn_dq_finish_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(dq32), n4, d_model / 4,
+               reinterpret_cast<uint16_t*>(dqkv16), bf16);
     MMT_LAUNCH_CHECK("attn_dq_finish_kernel");
+    const int gx = (d_model / 4 + 31) / 32;
+    int64_t want = (rows + 63) / 64;
+    const int64_t cap = 2 * num_sms() / gx + 1;
+    const int gy = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    launch_pdl(bwd::attn_colsum16_kernel, dim3(gx, gy), dim3(32, 8), 0, st, reinterpret_cast<const uint16_t*>(dqkv16), rows,
+               d_model, 3LL * d_model, 1.0f / scale16, dbias, bf16);
+    MMT_LAUNCH_CHECK("attn_colsum16_kernel");
   }
   return 0;
 }
