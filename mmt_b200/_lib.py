@@ -137,6 +137,7 @@ SIGNATURES = {
 }
 
 _lib = None
+_note = None      # optional callable(*tensors): test hook, see gemm16()
 
 
 def load():
@@ -222,26 +223,28 @@ def gemm16(dt, M, N, K, A, a_ld, a_mn, B, b_ld, b_mn, *, a_off=0, b_off=0, C32=N
            aux_off=0, aux_ld=0, epilogue=EPI_NONE, alpha=1.0, p_drop=0.0, seed=0, seed_ctr=None, site=0, batch=1,
            batch_inner=1, a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), bias_bs=0, colsum=None, colsum_off=0,
            colsum_scale=1.0, colsum_bs=0, split_k=False):
-  """C = epilogue(alpha * A B^T) on 16-bit operands (mmt_gemm16, include/mmt_b200.h).  Offsets in elements."""
-  d = GemmDesc16()
-  d.M, d.N, d.K, d.dtype = M, N, K, dt
-  d.A, d.a_ld, d.a_mn = ptr(A, a_off), a_ld, a_mn
-  d.B, d.b_ld, d.b_mn = ptr(B, b_off), b_ld, b_mn
-  d.C32, d.c32_ld = ptr(C32, c32_off), c32_ld
-  d.C16, d.c16_ld, d.out16_scale = ptr(C16, c16_off), c16_ld, out16_scale
-  d.bias = ptr(bias, bias_off)
-  d.add, d.add_ld = ptr(add, add_off), add_ld
-  d.aux16, d.aux_ld = ptr(aux16, aux_off), aux_ld
-  d.epilogue, d.alpha = epilogue, alpha
-  d.p_drop, d.site, d.seed, d.seed_ctr = p_drop, site, seed, seed_ctr
-  d.batch, d.batch_inner = batch, batch_inner
-  d.a_bs0, d.a_bs1 = a_bs
-  d.b_bs0, d.b_bs1 = b_bs
-  d.c_bs0, d.c_bs1 = c_bs
-  d.bias_bs = bias_bs
-  d.colsum, d.colsum_scale, d.colsum_bs = ptr(colsum, colsum_off), colsum_scale, colsum_bs
-  d.flags = GEMM_SPLIT_K if split_k else 0
-  check(load().mmt_gemm16(ctypes.byref(d), stream_ptr()), "mmt_gemm16")
+  """C = epilogue(alpha * A B^T) on 16-bit operands (mmt_gemm16, include/mmt_b200.h).  Offsets in elements.
+  ~75 calls per train step: the descriptor is filled by ONE positional constructor call (field order of
+  GemmDesc16._fields_) and pointers are computed inline."""
+  if _note is not None:                     # test hook (tests/test_abi_and_host.py records the tensors a call touches)
+    _note(A, B, C32, C16, bias, add, aux16, colsum)
+  d = GemmDesc16(
+      M, N, K, dt,
+      A.data_ptr() + 2 * a_off, a_ld, a_mn,
+      B.data_ptr() + 2 * b_off, b_ld, b_mn,
+      None if C32 is None else C32.data_ptr() + 4 * c32_off, c32_ld,
+      None if C16 is None else C16.data_ptr() + 2 * c16_off, c16_ld, out16_scale,
+      None if bias is None else bias.data_ptr() + 4 * bias_off,
+      None if add is None else add.data_ptr() + 4 * add_off, add_ld,
+      None if aux16 is None else aux16.data_ptr() + 2 * aux_off, aux_ld,
+      epilogue, alpha, p_drop, site, seed, seed_ctr, batch, batch_inner,
+      a_bs[0], a_bs[1], b_bs[0], b_bs[1], c_bs[0], c_bs[1], bias_bs,
+      None if colsum is None else colsum.data_ptr() + 4 * colsum_off, colsum_scale, colsum_bs,
+      GEMM_SPLIT_K if split_k else 0)
+  rc = load().mmt_gemm16(ctypes.byref(d), torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+                         if A.is_cuda else stream_ptr())
+  if rc != 0:
+    check(rc, "mmt_gemm16")
 
 
 def cast16(dt, src, rows, cols, in_ld, out, out_cols, out_ld, scale=1.0, p_drop=0.0, seed=0, seed_ctr=None, site=0,

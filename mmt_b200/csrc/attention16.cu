@@ -647,46 +647,51 @@ __global__ void __launch_bounds__(256) attn_delta16_kernel(const uint16_t* __res
   }
 }
 
-// dq32 [rows, d] -> the Q block of dqkv16 (16-bit, already in the scale16 domain); dq32 is left zeroed for the next
-// layer's accumulation.  Pure streaming, one float4 per thread (the Q bias gradient is a separate mmt_colsum16-style
-// pass over the 16-bit result: a fused column sum put one atomic per block and column on 128 hot addresses).
-__global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict__ dq32, int64_t n4, int d4,
-                                                            uint16_t* __restrict__ dqkv16, int bf16) {
+// dq32 [rows, d] -> the Q block of dqkv16 (16-bit, already in the scale16 domain), its bias-gradient column sums
+// (divided by scale16), and dq32 zeroed again for the next layer's accumulation.
+// One CTA owns FIN_ROWS consecutive rows and ALL d columns: thread (x, y) walks rows y, y+2, ... of its float4 column
+// x with four rows in flight, keeps the column sum in registers and the CTA issues ONE atomic per column -- the
+// first version flushed per warp-row-group and put ~1200 atomics on each of 128 hot addresses.
+constexpr int FIN_ROWS = 32;
+__global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict__ dq32, int64_t rows, int d4,
+                                                            uint16_t* __restrict__ dqkv16, float* __restrict__ dbias,
+                                                            float inv_scale16, int bf16) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float4 red[256];
+  const int x = threadIdx.x, y = threadIdx.y;                // blockDim = (d4 <= 128 ? d4 : 128, 256 / that)
+  const int ny = blockDim.y;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 g = dq32[i];
-    dq32[i] = zero;
-    const int64_t r = i / d4;
-    const int c4 = (int)(i - r * d4);
-    *reinterpret_cast<uint2*>(dqkv16 + r * 3 * (4 * (int64_t)d4) + 4 * c4) = pack4(g, bf16 != 0);
-  }
-}
-
-// out[n] += scale * sum_r X16[r*ld + n]   (bias gradient of the Q block)
-__global__ void __launch_bounds__(256) attn_colsum16_kernel(const uint16_t* __restrict__ X, int64_t rows, int n, int64_t ld,
-                                                            float scale, float* __restrict__ out, int bf16) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ float4 red[8][32];
-  const int c4 = blockIdx.x * 32 + threadIdx.x;
-  const int ty = threadIdx.y;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c4 * 4 < n) {
-    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows; r += (int64_t)gridDim.y * 8) {
-      const float4 v = unpack4(*reinterpret_cast<const uint2*>(X + r * ld + 4 * c4), bf16 != 0);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  for (int c4 = x; c4 < d4; c4 += blockDim.x) {
+    float4 acc = zero;
+    const int64_t r0 = (int64_t)blockIdx.x * FIN_ROWS;
+    for (int k = y; k < FIN_ROWS; k += 4 * ny) {
+      float4 g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = r0 + k + u * ny;
+        g[u] = (k + u * ny < FIN_ROWS && r < rows) ? dq32[r * d4 + c4] : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = r0 + k + u * ny;
+        if (k + u * ny < FIN_ROWS && r < rows) {
+          dq32[r * d4 + c4] = zero;
+          *reinterpret_cast<uint2*>(dqkv16 + r * 3 * (4 * (int64_t)d4) + 4 * c4) = pack4(g[u], bf16 != 0);
+          acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w;
+        }
+      }
     }
-  }
-  red[ty][threadIdx.x] = acc;
-  __syncthreads();
-  if (ty == 0 && c4 * 4 < n) {
-    for (int w = 1; w < 8; ++w) {
-      const float4 t = red[w][threadIdx.x];
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    red[y * blockDim.x + x] = acc;
+    __syncthreads();
+    if (y == 0) {
+      for (int w = 1; w < ny; ++w) {
+        const float4 t = red[w * blockDim.x + x];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      atomic_add4(dbias + 4 * c4, make_float4(acc.x * inv_scale16, acc.y * inv_scale16, acc.z * inv_scale16, acc.w * inv_scale16));
     }
-    atomic_add4(out + 4 * c4, make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale));
+    __syncthreads();
   }
 }
 }  // namespace bwd
@@ -805,19 +810,13 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);
   MMT_LAUNCH_CHECK("attention16_bwd_kernel");
   {
-    const int64_t n4 = rows * (d_model / 4);
-    int64_t blocks = (n4 + 255) / 256;
-    if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-    launch_pdl(bwd::attn_dq_finish_kernel, dim3((int)blocks), dim3(256), 0, st, reinterpret_cast<float4*>(dq32), n4, d_model / 4,
-               reinterpret_cast<uint16_t*>(dqkv16), bf16);
+    const int d4 = d_model / 4;
+    const int bx = d4 <= 128 ? d4 : 128;
+    const int by = 256 / bx > 0 ? 256 / bx : 1;
+    const int64_t blocks = (rows + bwd::FIN_ROWS - 1) / bwd::FIN_ROWS;
+    launch_pdl(bwd::attn_dq_finish_kernel, dim3((int)blocks), dim3(bx, by), 0, st, reinterpret_cast<float4*>(dq32), rows, d4,
+               reinterpret_cast<uint16_t*>(dqkv16), dbias, 1.0f / scale16, bf16);
     MMT_LAUNCH_CHECK("attn_dq_finish_kernel");
-    const int gx = (d_model / 4 + 31) / 32;
-    int64_t want = (rows + 63) / 64;
-    const int64_t cap = 2 * num_sms() / gx + 1;
-    const int gy = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-    launch_pdl(bwd::attn_colsum16_kernel, dim3(gx, gy), dim3(32, 8), 0, st, reinterpret_cast<const uint16_t*>(dqkv16), rows,
-               d_model, 3LL * d_model, 1.0f / scale16, dbias, bf16);
-    MMT_LAUNCH_CHECK("attn_colsum16_kernel");
   }
   return 0;
 }

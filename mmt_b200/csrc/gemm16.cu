@@ -30,10 +30,11 @@ namespace mmt {
 namespace {
 using namespace tc;
 
-constexpr int BM = 128, BN = 256, BNH = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BN_MAX = 256;                           // pair tile 256 x BN, BN = 256 or 128 (template parameter)
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BM * BK * 2, STAGE_BYTES = A_BYTES + (BN_MAX / 2) * BK * 2;   // ring slots sized for BN = 256
 constexpr int STG_PITCH = 36;                         // 32-column chunks (fp32 outputs)
 constexpr int STG_PITCH16 = 68;                       // 64-column chunks (16-bit-only outputs)
 constexpr uint32_t STG_BYTES_PER_WARP = 32 * STG_PITCH16 * 4;
@@ -52,10 +53,14 @@ __device__ __forceinline__ uint2 ldg_u2(const void* p) { return *reinterpret_cas
 // output-heavy, short-K products (QKV, FFN-up, GELU' dgrad: up to 2 x 86 MB written per launch); their epilogue
 // computes in the TMEM layout and moves data with TMA only (see the epilogue).  With per-lane global stores they
 // ran epilogue-bound at 1/3 - 1/2 of the tensor-core rate.
-template <bool OUT16>
+// BN: 256, or 128 when the 256-wide tiling would leave the last wave of CTA pairs half empty (N = 512 outputs of
+// 13952 rows: 110 tiles on 74 pairs = 2 rounds at 74 % -> 220 tiles = 3 rounds at 99 %).
+template <bool OUT16, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_x, const G16Args args) {
+  constexpr int BNH = BN / 2;
+  constexpr uint32_t TX_BYTES = A_BYTES + BNH * BK * 2;     // bytes one CTA receives per k-block
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -120,7 +125,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * TX_BYTES);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = (kb0 + i) * BK;
@@ -204,8 +209,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int row0 = m0 + (int)rank * BM + q * 32;
         const bool row_ok = row0 + lane < d.M;
         if (bias) {
-          const int bc = n0 + chalf * 128 + lane * 4;
-          const float4 b = bc < d.N ? __ldg(reinterpret_cast<const float4*>(bias + bc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int bc = n0 + chalf * BNH + lane * 4;
+          const float4 b = (lane * 4 < BNH && bc < d.N) ? __ldg(reinterpret_cast<const float4*>(bias + bc)) : make_float4(0.f, 0.f, 0.f, 0.f);
           __syncwarp();
           *reinterpret_cast<float4*>(sbias + lane * 4) = b;
           __syncwarp();
@@ -214,7 +219,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c = chalf * 2; c < chalf * 2 + 2; ++c) {
+        for (int c = chalf * (BN / 128); c < (chalf + 1) * (BN / 128); ++c) {
           const int col0 = n0 + c * 64;
           if (col0 >= d.N || (d.flags & 512)) break;         // warp-uniform (512: timing experiment, no epilogue)
           if (d.epilogue == MMT_EPI_DGELU && lane == 0) {    // GELU' operand tile: asynchronous, consumed below
@@ -235,7 +240,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
           }
           if (bias) {                                        // same 64 values for every lane: broadcast reads
-            const float* sb = sbias + (c & 1) * 64;
+            const float* sb = sbias + (c - chalf * (BN / 128)) * 64;
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
               const float4 b = *reinterpret_cast<const float4*>(sb + j);
@@ -608,6 +613,21 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   G16Args args;
   args.d = d;
   args.num_m_tiles = (d.M + 2 * BM - 1) / (2 * BM);
+  // tile width: 256 unless the narrower tiling fills the CTA-pair waves markedly better (see the kernel comment)
+  int BN = 256;
+  {
+    const int pairs_max = num_sms() / 2;
+    const auto eff = [&](int bn) {
+      const long t = (long)args.num_m_tiles * ((d.N + bn - 1) / bn) * d.batch;
+      const long rounds = (t + pairs_max - 1) / pairs_max;
+      return (double)t / (double)(rounds * pairs_max);
+    };
+    // ... and only for short K: at K = 3072 the narrower tile's extra A-operand traffic costs more than the wave gains
+    // (measured: O-proj K=512 28.7 -> 23.8 us, FFN-down K=3072 53.5 -> 58.8 us)
+    if (!(d.flags & MMT_GEMM_SPLIT_K) && d.N > 128 && d.K <= 1024 && eff(128) > 1.15 * eff(256)) BN = 128;
+    static const int force = [] { const char* e = getenv("MMT_GEMM16_BN"); return e ? atoi(e) : 0; }();   // A/B switch
+    if (force == 128 || force == 256) BN = force;
+  }
   args.num_n_tiles = (d.N + BN - 1) / BN;
   args.num_kb = (d.K + BK - 1) / BK;
   args.split_k = 1;
@@ -636,7 +656,7 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   const int bo = d.batch / d.batch_inner;
   int rc = make_map16(&ma, d.A, d.M, d.K, d.a_ld, d.a_mn != 0, BM, bo, d.batch_inner, d.a_bs0, d.a_bs1, d.dtype, "A");
   if (rc) return rc;
-  rc = make_map16(&mb, d.B, d.N, d.K, d.b_ld, d.b_mn != 0, BNH, bo, d.batch_inner, d.b_bs0, d.b_bs1, d.dtype, "B");
+  rc = make_map16(&mb, d.B, d.N, d.K, d.b_ld, d.b_mn != 0, BN / 2, bo, d.batch_inner, d.b_bs0, d.b_bs1, d.dtype, "B");
   if (rc) return rc;
   // 16-bit-only outputs take the 64-column epilogue (16-byte accesses, complete 128-byte lines)
   const bool out16 = d.C16 && !d.C32 && !d.add && d.p_drop == 0.f && args.split_k == 1 && (d.N % 8) == 0 &&
@@ -650,8 +670,10 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   {
     std::lock_guard<std::mutex> lk(mu);
     if (dev < 64 && !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(gemm16_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
       if (e != cudaSuccess) return cuda_status(e, "mmt_gemm16 smem attribute");
       configured[dev] = true;
     }
@@ -667,8 +689,10 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
       if (rc) return rc;
     }
   }
-  if (out16) launch_pdl(gemm16_kernel<true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
-  else launch_pdl(gemm16_kernel<false>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
+  if (out16 && BN == 256) launch_pdl(gemm16_kernel<true, 256>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
+  else if (out16) launch_pdl(gemm16_kernel<true, 128>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
+  else if (BN == 256) launch_pdl(gemm16_kernel<false, 256>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
+  else launch_pdl(gemm16_kernel<false, 128>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, ma, mb, mc, mx, args);
   MMT_LAUNCH_CHECK("gemm16_kernel");
   return 0;
 }

@@ -18,9 +18,13 @@ import torch
 from . import _lib
 
 
-class FusedAdam:
+class FusedAdam(torch.optim.Optimizer):
+  """A torch.optim.Optimizer (so lr schedulers / warm-up wrappers accept it) whose step is one fused kernel per
+  contiguous run of the flat parameter buffer."""
 
   def __init__(self, net, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    trainable = [p for p in net._hot_params() if p.requires_grad]
+    super().__init__(trainable, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
     self.net = net
     self.grad_scale = grad_scale
     self.t = 0
@@ -36,9 +40,7 @@ class FusedAdam:
     others = [p for p in net.parameters() if id(p) not in hot and p.requires_grad]
     self.other = torch.optim.Adam(others, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay) \
         if others else None
-    self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
-    group = dict(self.defaults, params=[p for p in net._hot_params() if p.requires_grad], initial_lr=lr)
-    self.param_groups = [group] + (self.other.param_groups if self.other is not None else [])
+    self.param_groups[0].setdefault("initial_lr", lr)
     self._runs = None
     self.step_ctr = None        # device uint64 pointer added to the bias-correction step (CUDA-graph replays)
 
@@ -50,6 +52,10 @@ class FusedAdam:
   @lr.setter
   def lr(self, v):
     self.param_groups[0]["lr"] = v
+
+  def _sync_hyper(self, opt):
+    for g in opt.param_groups:
+      g.update({k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")})
 
   def _compute_runs(self):
     """Contiguous [offset, end) ranges of the flat buffer whose parameters are trained."""
@@ -93,10 +99,11 @@ class FusedAdam:
     for s_, d_ in zip(self.sub, sd.get("sub", [])):
       s_.load_state_dict(d_)
 
-  def step(self):
+  @torch.no_grad()
+  def step(self, closure=None):
     net = self.net
     for sub in self.sub:
-      sub.param_groups[0].update({k: self.param_groups[0][k] for k in ("lr", "betas", "eps", "weight_decay")})
+      self._sync_hyper(sub)
       sub.step_ctr = self.step_ctr
       sub.step()
     if self.m.device != net.flat.device:
@@ -151,4 +158,5 @@ class FusedAdam:
       if w16 is not None and hasattr(net, "cfg"):
         w16.refresh_padded(net.cfg, net.flat)      # row-padded ReduceDim copies (two small casts)
     if self.other is not None:
+      self._sync_hyper(self.other)
       self.other.step()

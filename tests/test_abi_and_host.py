@@ -163,6 +163,7 @@ def recorder(monkeypatch):
     return real_ptr(t, offset)
 
   monkeypatch.setattr(_lib, "_lib", rec)
+  monkeypatch.setattr(_lib, "_note", lambda *ts: [rec.note(t) for t in ts])
   monkeypatch.setattr(_lib, "ptr", ptr)
   monkeypatch.setattr(engine, "ptr", ptr)
   monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
