@@ -527,15 +527,25 @@ def encode_backward(cfg, flat, gflat, sv, dvid, dtxt, dtw, need_dtext=True):
   return dtext
 
 
-def sims_forward(vid, txt, vw, tw, caps, merge_avg):
+SPLIT_DOTS_MIN = 256      # training batches at least this large take the tensor-core split products
+
+
+def sims_forward(vid, txt, vw, tw, caps, merge_avg, train_precision=None):
   """sharded_cross_view_inner_product (model.py:789-837).  vid [Nv,M,d], txt [Nq,M,d] (Nq = Nv*caps,
-  video-major), vw [Nv,M], tw [Nq,M] -> (sims, dots [M,Nq,Nv])."""
+  video-major), vw [Nv,M], tw [Nq,M] -> (sims, dots [M,Nq,Nv]).
+  The dot products are fp32 FMAs (ranking bit-exact against the reference on identical embeddings) except in
+  TRAINING with a 16-bit `train_precision` and a large batch (the data-parallel global batch), where they are
+  three-pass split tensor-core products of fp32-class accuracy (engine16.sims_dots_split)."""
   lib = _lib.load()
   Nv, M, d = vid.shape
   Nq = txt.shape[0]
-  dots = torch.empty((M, Nq, Nv), device=vid.device, dtype=torch.float32)
-  gemm(Nq, Nv, d, txt, M * d, 1, vid, M * d, 1, dots, Nv, batch=M, a_bs=(d, 0), b_bs=(d, 0),
-       c_bs=(Nq * Nv, 0))
+  if train_precision is not None and _lib.is16(train_precision) and Nv >= SPLIT_DOTS_MIN and Nv % 4 == 0 and d % 8 == 0:
+    from . import engine16
+    dots = engine16.sims_dots_split(_lib.dt_of(train_precision), vid, txt)
+  else:
+    dots = torch.empty((M, Nq, Nv), device=vid.device, dtype=torch.float32)
+    gemm(Nq, Nv, d, txt, M * d, 1, vid, M * d, 1, dots, Nv, batch=M, a_bs=(d, 0), b_bs=(d, 0),
+         c_bs=(Nq * Nv, 0))
   rows = Nv if (merge_avg and caps > 1) else Nq
   sims = torch.empty((rows, Nv), device=vid.device, dtype=torch.float32)
   check(lib.mmt_sims_combine_fwd(ptr(dots), ptr(tw), ptr(vw), Nq, Nv, M, caps,

@@ -447,6 +447,25 @@ def video_backward(cfg, flat, gflat, sv, dvid, on_layer_done=None):
                          ptr(gflat, L.off("video_dim_reduce.%s.fc.bias" % mod)), 1, st), "mmt_colsum")
 
 
+def sims_dots_split(dt, vid, txt):
+  """Per-expert dot products dots[m, i, j] = <txt[i, m], vid[j, m]> as three tensor-core passes over two-term splits
+  (x = hi + lo / 2048): fp32-class accuracy (~2^-21 relative).  TRAINING ONLY and only for large batches (the
+  data-parallel global batch): at N = 512 the fp32-FMA kernel takes 143 us per step on every rank.  Evaluation keeps
+  the fp32-FMA products (engine.sims_forward), whose ranking is bit-exact against the reference's."""
+  Nv, M, d = vid.shape
+  Nq = txt.shape[0]
+  v_h, v_l = _e16((Nv, M * d), vid, dt), _e16((Nv, M * d), vid, dt)
+  t_h, t_l = _e16((Nq, M * d), vid, dt), _e16((Nq, M * d), vid, dt)
+  cast16(dt, vid, Nv, M * d, M * d, v_h, M * d, M * d, out_lo=v_l)
+  cast16(dt, txt, Nq, M * d, M * d, t_h, M * d, M * d, out_lo=t_l)
+  dots = torch.empty((M, Nq, Nv), device=vid.device, dtype=torch.float32)
+  kw = dict(batch=M, a_bs=(d, 0), b_bs=(d, 0), c_bs=(Nq * Nv, 0), c32_ld=Nv)
+  lo = 1.0 / 2048.0
+  for i, (a, b, al) in enumerate(((t_h, v_h, 1.0), (t_h, v_l, lo), (t_l, v_h, lo))):
+    gemm16(dt, Nq, Nv, d, a, M * d, 0, b, M * d, 0, alpha=al, C32=dots, add=dots if i else None, add_ld=Nv, **kw)
+  return dots
+
+
 def sims_backward_products(dt, ddots, vid, txt, scale16):
   """The two gradient products of the similarity (engine.sims_backward):
   dtxt[:, m, :] = ddots_m @ vid_m ; dvid[:, m, :] = ddots_m^T @ txt_m.

@@ -83,7 +83,8 @@ class SimsFn(torch.autograd.Function):
   @staticmethod
   def forward(ctx, vid, txt, vw, tw, caps, merge_avg, bwd_precision=engine.PREC_FP32, scale16=1.0):
     vid, txt, vw, tw = vid.contiguous(), txt.contiguous(), vw.contiguous(), tw.contiguous()
-    sims, dots = engine.sims_forward(vid, txt, vw, tw, caps, merge_avg)
+    training = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])     # a gradient will be asked for
+    sims, dots = engine.sims_forward(vid, txt, vw, tw, caps, merge_avg, bwd_precision if training else None)
     ctx.save_for_backward(vid, txt, vw, tw, dots)
     ctx.caps, ctx.merge_avg, ctx.bwd_precision, ctx.scale16 = caps, merge_avg, bwd_precision, scale16
     return sims

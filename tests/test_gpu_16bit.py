@@ -367,3 +367,21 @@ def test_train_step_f16_with_dropout_and_fused_adam(dev):
     din = net.cfg.in_dims[k]
     ref = net._param("video_dim_reduce.%s.fc.weight" % net.cfg.mods[k]).half()
     assert torch.equal(t[:, :din], ref)
+
+
+def test_split_dot_products_match_fp32_fma_products(dev):
+  """Large training batches take the three-pass split tensor-core dot products (engine16.sims_dots_split): fp32-class
+  accuracy against the fp32-FMA kernel that evaluation (and small batches) use."""
+  from mmt_b200 import _lib, engine, engine16
+  g = torch.Generator().manual_seed(9)
+  Nv, M, d = 512, 7, 512
+  vid = torch.nn.functional.normalize(torch.randn(Nv, M, d, generator=g), dim=-1).to(dev)
+  txt = torch.nn.functional.normalize(torch.randn(Nv, M, d, generator=g), dim=-1).to(dev)
+  tw = torch.softmax(torch.randn(Nv, M, generator=g), -1).to(dev)
+  vw = torch.full((Nv, M), 1.0 / M, device=dev)
+  sims_ref, dots_ref = engine.sims_forward(vid, txt, vw, tw, 1, True)
+  sims, dots = engine.sims_forward(vid, txt, vw, tw, 1, True, _lib.PREC_F16)
+  ref64 = torch.einsum("imd,jmd->mij", txt.double(), vid.double())
+  e_split, e_fma = H.rel_err(dots, ref64), H.rel_err(dots_ref, ref64)
+  print("dot products N=512: split tensor-core %.2e, fp32 FMA %.2e (vs fp64)" % (e_split, e_fma))
+  assert e_split < 2e-6 and H.rel_err(sims, sims_ref) < 2e-6
