@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
+#include <unordered_set>
 
 #include "common.cuh"
 
@@ -32,6 +34,22 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize must be set once per (kernel, device): a per-device table instead of a
+// process-global latch, so a second GPU driven from the same process is configured too.
+int ensure_dynamic_smem(const void* fn, size_t bytes, const char* what) {
+  static std::mutex mu;
+  static std::unordered_set<uint64_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t key = (uint64_t)(uintptr_t)fn * 1315423911ull + (uint64_t)dev;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(key)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return cuda_status(e, what);
+  done.insert(key);
+  return 0;
 }
 
 int gemm_simt(const mmt_gemm_desc& d, cudaStream_t stream);

@@ -724,14 +724,6 @@ int make_map16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
   return 0;
 }
 
-int set_smem_once(const void* kern, size_t bytes, bool* flag, const char* what) {
-  if (*flag) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return cuda_status(e, what);
-  *flag = true;
-  return 0;
-}
-
 }  // namespace
 }  // namespace mmt
 
@@ -758,8 +750,7 @@ extern "C" int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t
   a.scale_log2 = scale * LOG2E;
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = dtype == MMT_DT_BF16 ? 1 : 0;
-  static bool configured = false;
-  rc = set_smem_once((const void*)fwd::attention16_fwd_kernel, fwd::SMEM, &configured, "attention16_fwd smem attribute");
+  rc = ensure_dynamic_smem((const void*)fwd::attention16_fwd_kernel, fwd::SMEM, "attention16_fwd smem attribute");
   if (rc) return rc;
   dim3 grid((S + fwd::QM - 1) / fwd::QM, H, B);
   launch_pdl(fwd::attention16_fwd_kernel, grid, dim3(fwd::THREADS), fwd::SMEM, (cudaStream_t)stream, mq, mk, a);
@@ -803,8 +794,7 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.inv_scale16 = 1.0f / scale16;
   a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = bf16;
-  static bool configured = false;
-  rc = set_smem_once((const void*)bwd::attention16_bwd_kernel, bwd::SMEM, &configured, "attention16_bwd smem attribute");
+  rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel, bwd::SMEM, "attention16_bwd smem attribute");
   if (rc) return rc;
   dim3 grid((S + bwd::KT - 1) / bwd::KT, H, B);
   launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);

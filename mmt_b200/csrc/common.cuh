@@ -36,6 +36,7 @@ int cuda_status(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+int ensure_dynamic_smem(const void* fn, size_t bytes, const char* what);   // once per (kernel, device)
 
 // ---- warp helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ int warp_sum_int(int v) {

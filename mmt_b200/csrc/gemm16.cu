@@ -663,20 +663,11 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
                      ((d.c16_ld | d.c_bs0 | d.c_bs1 | d.bias_bs | d.colsum_bs) % 8) == 0 && ((uintptr_t)d.C16 % 16) == 0 &&
                      (!d.aux16 || ((d.aux_ld % 8) == 0 && ((uintptr_t)d.aux16 % 16) == 0)) &&
                      (!d.bias || ((uintptr_t)d.bias % 16) == 0) && (!d.colsum || ((uintptr_t)d.colsum % 16) == 0);
-  static std::mutex mu;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
   {
-    std::lock_guard<std::mutex> lk(mu);
-    if (dev < 64 && !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm16_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm16_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-      if (e != cudaSuccess) return cuda_status(e, "mmt_gemm16 smem attribute");
-      configured[dev] = true;
-    }
+    const void* fn = out16 ? (BN == 256 ? (const void*)gemm16_kernel<true, 256> : (const void*)gemm16_kernel<true, 128>)
+                           : (BN == 256 ? (const void*)gemm16_kernel<false, 256> : (const void*)gemm16_kernel<false, 128>);
+    rc = ensure_dynamic_smem(fn, SMEM_BYTES, "mmt_gemm16 smem attribute");
+    if (rc) return rc;
   }
   const int work = tiles * args.split_k * d.batch;
   const int pairs = work < max_pairs ? work : max_pairs;

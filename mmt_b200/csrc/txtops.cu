@@ -398,12 +398,8 @@ int mmt_txt_attention_fwd(const void* qkv16, const float* mask, int32_t R, int32
   if (rc) return rc;
   MMT_ARG_CHECK(ctx16 != nullptr, MMT_E_ARG, "mmt_txt_attention_fwd: null output");
   const size_t smem = sizeof(float) * (3 * (size_t)W * TPITCH + W);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(txt_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    if (e != cudaSuccess) return cuda_status(e, "txt_attention_fwd smem attribute");
-    configured = true;
-  }
+  rc = ensure_dynamic_smem((const void*)txt_attention_fwd_kernel, 110 * 1024, "txt_attention_fwd smem attribute");
+  if (rc) return rc;
   launch_pdl(txt_attention_fwd_kernel, dim3(H, R), dim3(128), smem, (cudaStream_t)stream, a, reinterpret_cast<uint16_t*>(ctx16));
   MMT_LAUNCH_CHECK("txt_attention_fwd");
   return 0;
@@ -417,12 +413,8 @@ int mmt_txt_attention_bwd(const void* qkv16, const void* dctx16, const float* ma
   if (rc) return rc;
   MMT_ARG_CHECK(dctx16 && dqkv16, MMT_E_ARG, "mmt_txt_attention_bwd: null pointer");
   const size_t smem = sizeof(float) * (4 * (size_t)W * TPITCH + 2 * (size_t)W * (W + 1) + W);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(txt_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) return cuda_status(e, "txt_attention_bwd smem attribute");
-    configured = true;
-  }
+  rc = ensure_dynamic_smem((const void*)txt_attention_bwd_kernel, 220 * 1024, "txt_attention_bwd smem attribute");
+  if (rc) return rc;
   launch_pdl(txt_attention_bwd_kernel, dim3(H, R), dim3(128), smem, (cudaStream_t)stream, a,
              reinterpret_cast<const uint16_t*>(dctx16), reinterpret_cast<uint16_t*>(dqkv16));
   MMT_LAUNCH_CHECK("txt_attention_bwd");

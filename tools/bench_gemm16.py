@@ -15,8 +15,12 @@ def bench(name, M, N, K, a_mn=0, b_mn=0, reps=5, iters=20, dbg=0, **kw):
   A = [torch.randn((K, M) if a_mn else (M, K), device=dev).to(tdt) for _ in range(reps)]
   B = [(torch.randn((K, N) if b_mn else (N, K), device=dev) * 0.05).to(tdt) for _ in range(reps)]
   out32 = [torch.empty(M, N, device=dev) for _ in range(reps)] if kw.get("c32") else None
-  out16 = [torch.empty(M, N, device=dev, dtype=tdt) for _ in range(reps)] if kw.get("c16") else None
-  aux = [torch.randn(M, N, device=dev).to(tdt) for _ in range(reps)] if kw.get("epi") else None
+  pitch = kw.get("pitch", N)               # row pitch of the 16-bit outputs (elements); "inter": aux in the same rows
+  out16 = [torch.empty(M, pitch, device=dev, dtype=tdt) for _ in range(reps)] if kw.get("c16") else None
+  if kw.get("epi") and kw.get("inter"):
+    aux = None
+  else:
+    aux = [torch.randn(M, pitch, device=dev).to(tdt) for _ in range(reps)] if kw.get("epi") else None
   add = [torch.randn(M, N, device=dev) for _ in range(reps)] if kw.get("add") else None
   bias = torch.randn(N, device=dev)
   cs = torch.zeros(N, device=dev) if kw.get("colsum") else None
@@ -28,10 +32,11 @@ def bench(name, M, N, K, a_mn=0, b_mn=0, reps=5, iters=20, dbg=0, **kw):
     d.A, d.a_ld, d.a_mn = A[i].data_ptr(), (M if a_mn else K), a_mn
     d.B, d.b_ld, d.b_mn = B[i].data_ptr(), (N if b_mn else K), b_mn
     if out32: d.C32, d.c32_ld = out32[i].data_ptr(), N
-    if out16: d.C16, d.c16_ld, d.out16_scale = out16[i].data_ptr(), N, 1.0
+    if out16: d.C16, d.c16_ld, d.out16_scale = out16[i].data_ptr(), pitch, 1.0
     if not kw.get("split"): d.bias = bias.data_ptr()
     if add: d.add, d.add_ld = add[i].data_ptr(), N
-    if aux: d.aux16, d.aux_ld = aux[i].data_ptr(), N
+    if aux: d.aux16, d.aux_ld = aux[i].data_ptr(), pitch
+    elif kw.get("epi"): d.aux16, d.aux_ld = out16[i].data_ptr() + 2 * N, pitch
     d.epilogue = kw.get("epi", 0)
     d.alpha = 1.0
     d.p_drop, d.seed, d.site = kw.get("p", 0.0), 5, 3
@@ -69,6 +74,15 @@ if __name__ == "__main__":
     bench("dW1 wgrad split-K", 3072, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
     bench("dWqkv wgrad split-K", 1536, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
     bench("dWo wgrad split-K", 512, 512, BS, a_mn=1, b_mn=1, c32=1, split=1)
+  if which == "pitch":
+    bench("plain C16 pitch N", BS, 3072, 512, c16=1)
+    bench("plain C16 pitch 2N", BS, 3072, 512, c16=1, pitch=6144)
+    bench("GELU separate tensors", BS, 3072, 512, c16=1, epi=1)
+    bench("GELU separate, pitch 2N", BS, 3072, 512, c16=1, epi=1, pitch=6144)
+    bench("GELU interleaved rows [f|g]", BS, 3072, 512, c16=1, epi=1, pitch=6144, inter=1)
+    bench("plain C32", BS, 3072, 512, c32=1)
+    bench("N=1536 plain C16", BS, 1536, 512, c16=1)
+    bench("N=1536 plain C16 pitch 2N", BS, 1536, 512, c16=1, pitch=3072)
   if which == "ffnup":
     bench("FFN-up GELU (aux16+C16)", BS, 3072, 512, c16=1, epi=1, iters=3)
     bench("QKV fwd (C16)", BS, 1536, 512, c16=1, iters=3)
