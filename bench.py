@@ -383,26 +383,32 @@ def run_b200(args):
     # exposed; one graph launch is not.  The staged batch is copied device-to-device into the
     # graph's static inputs (inside the timed region).
     from mmt_b200.graph import GraphedTrainStep
-    skw = {k: ({m: t.clone() for m, t in v.items()} if isinstance(v, dict) else v)
-           for k, v in slots[0][0].items()}
-    g2 = GraphedTrainStep(net, crit, opt, skw, slots[0][1].clone(), lambda t: setattr(feed, "cls", t))
+    # TWO captures, one per staging slot: the slot's device tensors ARE the graph's static inputs, so the pinned-host
+    # batch is copied H2D straight into the inputs of the graph that runs next -- no device-to-device hop.  The
+    # two graphs share the net, the optimizer and one device-side step counter.
+    def set_text(t):
+      feed.cls = t
+    g_a = GraphedTrainStep(net, crit, opt, slots[0][0], slots[0][1], set_text)
+    g_b = GraphedTrainStep(net, crit, opt, slots[1][0], slots[1][1], set_text, share_with=g_a)
+    graphs = [g_a, g_b]
     stage(0, batches[0])
 
     def e2e_graph_step(i):
       slot = i & 1
       torch.cuda.current_stream().wait_event(ready[slot])
-      stage(slot ^ 1, batches[(i + 1) % NB])           # H2D of the next batch overlaps this step
-      g2.load(*slots[slot])
-      last["loss"] = g2.replay().item()                # device -> host read of the result
+      stage(slot ^ 1, batches[(i + 1) % NB])           # H2D of the next batch into the OTHER graph's inputs
+      last["loss"] = graphs[slot].replay().item()      # device -> host read of the result
 
     for i in range(2):
       e2e_graph_step(i)
     ms_g = timed(lambda i: e2e_graph_step(i + 2), args.steps)
-    g2.close()
+    g_b.close()
+    g_a.close()
     if ms_g < ms_e2e:
       ms_e2e = ms_g
       e2e_value = B * world * args.steps / (ms_g / 1e3)
-      e2e_api = "mmt_b200.graph.GraphedTrainStep.load + replay (whole step as one CUDA graph)"
+      e2e_api = ("mmt_b200.graph.GraphedTrainStep x2 (one capture per input slot, shared step counter): H2D into the "
+                 "idle graph's static inputs + replay")
 
   res = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -350,15 +350,19 @@ struct AttBwdArgs {
 
 namespace bwd {
 constexpr int KT = 128, QT = 128;
-constexpr int THREADS = 320;                         // TMA warp, MMA warp, 8 softmax warps
+// TMA warp, MMA warp, NSW softmax warps (8 or 16: PARTS = NSW / 4 warps share a TMEM lane quarter and split the columns)
 constexpr uint32_t TILE = 128 * DH * 2;              // 32 KB: 2 sub-tiles [128 rows x 128 B]
 constexpr uint32_t SUB = 128 * 128;                  // 16 KB
 constexpr size_t SMEM = 6 * TILE + 1024 /*align*/ + 128 /*barriers*/ + 2 * QT * 4;
 constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 384, TM_DQ = 0;
 
-__global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv,
+template <int NSW>
+__global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                      const __grid_constant__ CUtensorMap map_do,
                                                                      const AttBwdArgs args) {
+  constexpr int SMT = NSW * 32;                       // softmax threads
+  constexpr int PARTS = NSW / 4;                      // column parts per lane quarter
+  constexpr int PCOLS = 128 / PARTS;                  // columns of a 128-wide accumulator per part
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -372,9 +376,9 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;
   uint64_t* st_full = bars + 2;              // S^T and dPd^T in TMEM
-  uint64_t* pds_full = bars + 3;             // Pd^T / dS^T tiles written (256 arrivals)
+  uint64_t* pds_full = bars + 3;             // Pd^T / dS^T tiles written (SMT arrivals)
   uint64_t* mma2_done = bars + 4;            // dV / dK / dQ MMAs of this query tile complete
-  uint64_t* dq_drained = bars + 5;           // dQ read out of TMEM (256 arrivals)
+  uint64_t* dq_drained = bars + 5;           // dQ read out of TMEM (SMT arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_lse2 = reinterpret_cast<float*>(bars + 16);       // [QT] log2-domain lse of the query tile (+inf: no such query)
   float* s_delta = s_lse2 + QT;
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(st_full, 1);
-    mbar_init(pds_full, 256); mbar_init(mma2_done, 1); mbar_init(dq_drained, 256);
+    mbar_init(pds_full, SMT); mbar_init(mma2_done, 1); mbar_init(dq_drained, SMT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
@@ -468,9 +472,9 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
       }
     }
   } else {
-    // ===================== softmax backward + epilogues (warps 2..9) =====================
+    // ===================== softmax backward + epilogues (warps 2 .. 2+NSW) =====================
     const int q4 = warp & 3;                                   // TMEM lane quarter
-    const int half = (warp - 2) >> 2;                          // which 64 of the 128 columns
+    const int part = (warp - 2) >> 2;                          // which PCOLS of the 128 columns
     const int r = q4 * 32 + lane;                              // key row within the tile == TMEM lane
     const int key = k0 + r;
     const bool key_ok = key < S;
@@ -489,19 +493,19 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
     for (int i = 0; i < nqt; ++i) {
       const int qbase = i * QT;
       // per-query vectors of this tile (the previous tile's readers are past pds_full of i-1 ... and its dQ drain)
-      for (int t = threadIdx.x - 64; t < QT; t += 256) {
+      for (int t = threadIdx.x - 64; t < QT; t += SMT) {
         const int qq = qbase + t;
         const bool ok = qq < S;
         s_lse2[t] = ok ? __ldg(args.lse + ((int64_t)b * H + h) * S + qq) * LOG2E : INFINITY;
         s_delta[t] = ok ? __ldg(args.delta + ((int64_t)b * H + h) * S + qq) : 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
       mbar_wait(st_full, i & 1);
       tc_fence_after();
-      // 16 query columns at a time; the two column halves take alternate 16-column chunks so that a ragged last
-      // query tile (S = 218: 90 of 128 columns) leaves both with the same amount of work
+      // 16 query columns at a time; the column parts take interleaved 16-column chunks so that a ragged last
+      // query tile (S = 218: 90 of 128 columns) leaves them with (nearly) the same amount of work
 #pragma unroll 1
-      for (int cc = half; cc < 8; cc += 2) {
+      for (int cc = part; cc < 8; cc += PARTS) {
         const int col = cc * 16;
         const uint32_t rb = (uint32_t)(cc >> 2) * SUB + (uint32_t)r * 128;      // sub-tile (64 queries), this key's row
         const uint32_t ch0 = (uint32_t)((cc & 3) * 2), sw = (uint32_t)(r & 7);
@@ -548,16 +552,16 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
       fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ_i out of TMEM: lane = query row, this thread's 64 of the dh columns
+      // dQ_i out of TMEM: lane = query row, this thread's PCOLS of the dh columns
       mbar_wait(mma2_done, i & 1);
       tc_fence_after();
       {
         const int qq = qbase + r;
-        float* drow = args.dq32 + ((int64_t)b * S + qq) * d_model + h * DH + half * 64;
+        float* drow = args.dq32 + ((int64_t)b * S + qq) * d_model + h * DH + part * PCOLS;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PCOLS / 16; ++c) {
           float v[16];
-          tmem_ld16f(tmem + TM_DQ + lane_addr + half * 64 + c * 16, v);
+          tmem_ld16f(tmem + TM_DQ + lane_addr + part * PCOLS + c * 16, v);
           if (qq < S) {
 #pragma unroll
             for (int t = 0; t < 16; t += 4)
@@ -573,12 +577,12 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd_kernel(const __gri
     for (int which = 0; which < 2; ++which) {
       const uint32_t tm = which == 0 ? TM_DV : TM_DK;
       const int blk = which == 0 ? 2 : 1;                       // column block of dqkv16: Q | K | V
-      uint16_t* orow = args.dqkv16 + ((int64_t)b * S + key) * (3 * d_model) + blk * d_model + h * DH + half * 64;
-      float* bsum = args.dbias + blk * d_model + h * DH + half * 64;
+      uint16_t* orow = args.dqkv16 + ((int64_t)b * S + key) * (3 * d_model) + blk * d_model + h * DH + part * PCOLS;
+      float* bsum = args.dbias + blk * d_model + h * DH + part * PCOLS;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < PCOLS / 16; ++c) {
         float v[16];
-        tmem_ld16f(tmem + tm + lane_addr + half * 64 + c * 16, v);
+        tmem_ld16f(tmem + tm + lane_addr + part * PCOLS + c * 16, v);
         if (key_ok) {
           uint4 o0, o1;
           o0.x = pack2(v[0], v[1], bf16);   o0.y = pack2(v[2], v[3], bf16);
@@ -794,10 +798,20 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.inv_scale16 = 1.0f / scale16;
   a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = bf16;
-  rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel, bwd::SMEM, "attention16_bwd smem attribute");
-  if (rc) return rc;
+  static const int nsw = [] {                          // softmax warps per CTA (A/B switch; 8 is the measured default)
+    const char* e = getenv("MMT_ATT_BWD_WARPS");
+    return e && atoi(e) == 16 ? 16 : 8;
+  }();
   dim3 grid((S + bwd::KT - 1) / bwd::KT, H, B);
-  launch_pdl(bwd::attention16_bwd_kernel, grid, dim3(bwd::THREADS), bwd::SMEM, st, mqkv, mdo, a);
+  if (nsw == 16) {
+    rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel<16>, bwd::SMEM, "attention16_bwd smem attribute");
+    if (rc) return rc;
+    launch_pdl(bwd::attention16_bwd_kernel<16>, grid, dim3(64 + 16 * 32), bwd::SMEM, st, mqkv, mdo, a);
+  } else {
+    rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel<8>, bwd::SMEM, "attention16_bwd smem attribute");
+    if (rc) return rc;
+    launch_pdl(bwd::attention16_bwd_kernel<8>, grid, dim3(64 + 8 * 32), bwd::SMEM, st, mqkv, mdo, a);
+  }
   MMT_LAUNCH_CHECK("attention16_bwd_kernel");
   {
     const int d4 = d_model / 4;

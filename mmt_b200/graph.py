@@ -19,7 +19,7 @@ class GraphedTrainStep:
   set_text(t)    : hands the static text-feature tensor to whatever stands for txt_bert
   """
 
-  def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3):
+  def __init__(self, net, crit, opt, kwargs, text, set_text, warmup=3, share_with=None):
     import os
     if getattr(net, "_dp", False) and os.environ.get("MMT_GRAPH_DP", "0") != "1":
       # Capturing the data-parallel step (NCCL all-gather / all-reduce nodes inside the graph) is EXPERIMENTAL: the
@@ -30,7 +30,12 @@ class GraphedTrainStep:
     self.net, self.crit, self.opt = net, crit, opt
     self.kw, self.text = kwargs, text
     dev = net.flat.device
-    self.ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+    # `share_with`: another GraphedTrainStep over the SAME net / optimizer whose step counter this one joins.  Two
+    # captures with their own static input buffers let the host stage batch i+1 straight into the idle graph's
+    # inputs (H2D, no device-to-device copy) while graph i runs; one shared counter keeps dropout seeds and Adam's
+    # bias correction advancing by one per replay of either graph.
+    self.shared = share_with is not None
+    self.ctr = share_with.ctr if self.shared else torch.zeros(1, dtype=torch.int64, device=dev)
     self._attach()
     set_text(self.text)
 
@@ -102,6 +107,9 @@ class GraphedTrainStep:
     """Back to eager launches: detach the device counter and fold its value into the host-side
     step counts so Adam's bias correction continues where the replays left off."""
     torch.cuda.synchronize()
+    if self.shared:                   # the owner of the counter does the bookkeeping
+      self.ctr = None
+      return
     n = int(self.ctr.item())
     self._detach()
     self.ctr = None
