@@ -28,6 +28,7 @@
 #include "cvt16.cuh"
 #include "rowvec.cuh"
 #include "tc_ptx.cuh"
+#include "pair_ptx.cuh"
 
 namespace mmt {
 namespace {
@@ -129,6 +130,7 @@ constexpr size_t SMEM = Q_BYTES + KV_BYTES + 1024 /*align*/ + 128 /*barriers*/ +
 
 __global__ void __launch_bounds__(THREADS, 2) attention16_fwd_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                      const __grid_constant__ CUtensorMap map_k,
+                                                                     const __grid_constant__ CUtensorMap map_o,
                                                                      const AttArgs args) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -304,20 +306,28 @@ __global__ void __launch_bounds__(THREADS, 2) attention16_fwd_kernel(const __gri
     mbar_wait(o_full, (nblk - 1) & 1);
     tc_fence_after();
     const float inv_l = args.inv_keep / l_run;
-    uint16_t* orow = args.ctx16 + ((int64_t)b * S + qi) * d_model + h * DH;
+    // context tile -> the Q buffer (dead: every score MMA has completed), 128-byte-swizzled, -> two TMA stores clipped at
+    // S by the [B, S, d] map.  (Per-lane 16-byte stores to rows 1 KB apart take 32 LSU wavefronts per instruction.)
+    const uint32_t sq_u = smem_u32(sq);
+    const uint32_t rrow = (uint32_t)r;                          // query row within the tile == TMEM lane
 #pragma unroll 1
     for (int c = 0; c < DH / 16; ++c) {
       float v[16];
       tmem_ld16f(tmem + TM_O + lane_addr + c * 16, v);
-      if (row_ok) {
-        uint4 o0, o1;
-        o0.x = pack2(v[0] * inv_l, v[1] * inv_l, bf16);   o0.y = pack2(v[2] * inv_l, v[3] * inv_l, bf16);
-        o0.z = pack2(v[4] * inv_l, v[5] * inv_l, bf16);   o0.w = pack2(v[6] * inv_l, v[7] * inv_l, bf16);
-        o1.x = pack2(v[8] * inv_l, v[9] * inv_l, bf16);   o1.y = pack2(v[10] * inv_l, v[11] * inv_l, bf16);
-        o1.z = pack2(v[12] * inv_l, v[13] * inv_l, bf16); o1.w = pack2(v[14] * inv_l, v[15] * inv_l, bf16);
-        *reinterpret_cast<uint4*>(orow + c * 16) = o0;
-        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
-      }
+      const uint32_t rb = sq_u + (uint32_t)(c >> 2) * QSUB + rrow * 128;
+      const uint32_t ch0 = (uint32_t)((c & 3) * 2), sw = rrow & 7;
+      sts128u(rb + ((ch0 ^ sw) << 4), pack2(v[0] * inv_l, v[1] * inv_l, bf16), pack2(v[2] * inv_l, v[3] * inv_l, bf16),
+              pack2(v[4] * inv_l, v[5] * inv_l, bf16), pack2(v[6] * inv_l, v[7] * inv_l, bf16));
+      sts128u(rb + (((ch0 + 1) ^ sw) << 4), pack2(v[8] * inv_l, v[9] * inv_l, bf16), pack2(v[10] * inv_l, v[11] * inv_l, bf16),
+              pack2(v[12] * inv_l, v[13] * inv_l, bf16), pack2(v[14] * inv_l, v[15] * inv_l, bf16));
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      tma_store_3d(&map_o, sq_u, h * DH, q0, b);
+      tma_store_3d(&map_o, sq_u + QSUB, h * DH + 64, q0, b);
+      bulk_commit();
+      bulk_wait_read0();
     }
     if (row_ok && args.lse) args.lse[((int64_t)b * H + h) * S + qi] = (m_run + log2f(l_run)) * 0.69314718055994530942f;
     tc_fence_before();
@@ -346,6 +356,9 @@ struct AttBwdArgs {
   const uint64_t* ctr;
   uint32_t site;
   int bf16;
+  int dq_mode;            // 0: fp32 atomics into dq32 + attn_dq_finish_kernel (any S); 1: one key tile, dQ final in-kernel;
+                          // 2: two key tiles = a 2-CTA cluster, partial handed over through dq32 (see the kernel)
+  int debug;              // timing experiments (MMT_ATT_BWD_DEBUG): 1 no dQ atomics, 2 no softmax math, 4 no dV/dK stores
 };
 
 namespace bwd {
@@ -356,9 +369,40 @@ constexpr uint32_t SUB = 128 * 128;                  // 16 KB
 constexpr size_t SMEM = 6 * TILE + 1024 /*align*/ + 128 /*barriers*/ + 2 * QT * 4;
 constexpr uint32_t TM_ST = 0, TM_DP = 128, TM_DV = 256, TM_DK = 384, TM_DQ = 0;
 
+// column sums of a [32 rows (lanes) x 16 columns] register block by a halving butterfly (16 + 8 + 4 + 2 + 1 shuffles);
+// lane L (even) ends up with column bitrev4(L >> 1) and adds it to dst
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane, float* dst, float scale) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float send = (lane & 16) ? v[t] : v[t + 8], keep = (lane & 16) ? v[t + 8] : v[t];
+    v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float send = (lane & 8) ? v[t] : v[t + 4], keep = (lane & 8) ? v[t + 4] : v[t];
+    v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const float send = (lane & 4) ? v[t] : v[t + 2], keep = (lane & 4) ? v[t + 2] : v[t];
+    v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 1) == 0) {
+    const int colid = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    atomicAdd(dst + colid, v[0] * scale);
+  }
+}
+
 template <int NSW>
 __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                                      const __grid_constant__ CUtensorMap map_do,
+                                                                     const __grid_constant__ CUtensorMap map_out,
+                                                                     const __grid_constant__ CUtensorMap map_dq,
                                                                      const AttBwdArgs args) {
   constexpr int SMT = NSW * 32;                       // softmax threads
   constexpr int PARTS = NSW / 4;                      // column parts per lane quarter
@@ -379,6 +423,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
   uint64_t* pds_full = bars + 3;             // Pd^T / dS^T tiles written (SMT arrivals)
   uint64_t* mma2_done = bars + 4;            // dV / dK / dQ MMAs of this query tile complete
   uint64_t* dq_drained = bars + 5;           // dQ read out of TMEM (SMT arrivals)
+  uint64_t* xch_bar = bars + 6;              // dq_mode 2: the peer CTA's dQ partial of a query tile is in dq32 (one remote arrival)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_lse2 = reinterpret_cast<float*>(bars + 16);       // [QT] log2-domain lse of the query tile (+inf: no such query)
   float* s_delta = s_lse2 + QT;
@@ -394,6 +439,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1); mbar_init(qdo_full, 1); mbar_init(st_full, 1);
     mbar_init(pds_full, SMT); mbar_init(mma2_done, 1); mbar_init(dq_drained, SMT);
+    mbar_init(xch_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
@@ -401,6 +447,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (args.dq_mode == 2) cluster_sync_all();          // the peer's xch_bar is initialised before anyone arrives on it
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_wait();
@@ -490,6 +537,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
     const uint32_t prow0 = (uint32_t)(((int64_t)b * H + h) * S);
     // Pd^T / dS^T tiles: sub-tile = 64 queries, row = key, 16-byte chunk c of a row stored at c ^ (row & 7)
     const uint32_t sp_u = smem_u32(sp), sds_u = smem_u32(sds);
+    uint32_t xphase = 0;
     for (int i = 0; i < nqt; ++i) {
       const int qbase = i * QT;
       // per-query vectors of this tile (the previous tile's readers are past pds_full of i-1 ... and its dQ drain)
@@ -499,6 +547,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
         s_lse2[t] = ok ? __ldg(args.lse + ((int64_t)b * H + h) * S + qq) * LOG2E : INFINITY;
         s_delta[t] = ok ? __ldg(args.delta + ((int64_t)b * H + h) * S + qq) : 0.f;
       }
+      if (threadIdx.x == 64 && i > 0) bulk_wait_read0();      // dQ_{i-1}'s TMA reduction has read the Pd^T / dS^T buffers
       asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
       mbar_wait(st_full, i & 1);
       tc_fence_after();
@@ -509,7 +558,7 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
         const int col = cc * 16;
         const uint32_t rb = (uint32_t)(cc >> 2) * SUB + (uint32_t)r * 128;      // sub-tile (64 queries), this key's row
         const uint32_t ch0 = (uint32_t)((cc & 3) * 2), sw = (uint32_t)(r & 7);
-        if (qbase + col >= S || k0 + q4 * 32 >= S) {            // no such queries / no such keys in this warp: zeros
+        if (qbase + col >= S || k0 + q4 * 32 >= S || (args.debug & 2)) {   // no such queries / no such keys in this warp: zeros
           sts128u(sp_u + rb + ((ch0 ^ sw) << 4), 0u, 0u, 0u, 0u);
           sts128u(sp_u + rb + (((ch0 + 1) ^ sw) << 4), 0u, 0u, 0u, 0u);
           sts128u(sds_u + rb + ((ch0 ^ sw) << 4), 0u, 0u, 0u, 0u);
@@ -552,101 +601,181 @@ __global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd_kernel(const
       fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ_i out of TMEM: lane = query row, this thread's PCOLS of the dh columns
+      // dQ_i out of TMEM: lane = query row, this thread's PCOLS of the dh columns.
+      //   dq_mode 0 (more than two key tiles): fp32 atomics into the zeroed dq32; attn_dq_finish_kernel rounds it.
+      //   dq_mode 2 (two key tiles = the two CTAs of a cluster): the CTAs take turns -- for query tile i, CTA (i+1)&1
+      //     stores its partial to dq32 (plain stores, L2) and arrives on the other's xch_bar; CTA i&1 adds that to its
+      //     own TMEM partial and writes the final 16-bit dQ and the Q-bias column sums.  No zeroing, no atomics, no
+      //     extra kernel (the finish kernel cost 20 us per layer: 71 MB of traffic for 14 MB of result).
+      //   dq_mode 1 (one key tile): final directly.
       mbar_wait(mma2_done, i & 1);
       tc_fence_after();
       {
         const int qq = qbase + r;
+        const bool q_ok = qq < S;
         float* drow = args.dq32 + ((int64_t)b * S + qq) * d_model + h * DH + part * PCOLS;
-#pragma unroll 1
-        for (int c = 0; c < PCOLS / 16; ++c) {
-          float v[16];
-          tmem_ld16f(tmem + TM_DQ + lane_addr + part * PCOLS + c * 16, v);
-          if (qq < S) {
+        const bool finalize = args.dq_mode == 1 || (args.dq_mode == 2 && (i & 1) == kt);
+        if (!finalize && args.dq_mode == 0) {
+          // fp32 [128 queries x 128] tile staged in the Pd^T / dS^T buffers (free until the next softmax; four 128-byte-
+          // swizzled boxes of 32 columns) and ADDED to dq32 by TMA (cp.reduce.async.bulk: whole lines, clipped at S).
+          // Per-lane float4 atomics on rows 2 KB apart cost 32 LSU wavefronts per instruction: ~2 us per tile.
 #pragma unroll
-            for (int t = 0; t < 16; t += 4)
-              atomicAdd(reinterpret_cast<float4*>(drow + c * 16 + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+          for (int c = 0; c < PCOLS / 16; ++c) {
+            float v[16];
+            tmem_ld16f(tmem + TM_DQ + lane_addr + part * PCOLS + c * 16, v);
+            const int col = part * PCOLS + c * 16;
+            const uint32_t rb = sp_u + (uint32_t)(col >> 5) * (128 * 128) + (uint32_t)r * 128;
+            const uint32_t ch0 = (uint32_t)((col & 31) >> 2), sw = (uint32_t)(r & 7);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              sts128(rb + (((ch0 + t) ^ sw) << 4), make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]));
           }
+          tc_fence_before();
+          mbar_arrive(dq_drained);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+          if (threadIdx.x == 64 && !(args.debug & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_reduce_add_3d(&map_dq, sp_u + j * (128 * 128), h * DH + 32 * j, qbase, b);
+            bulk_commit();
+          }
+        } else if (!finalize) {
+#pragma unroll 1
+          for (int c = 0; c < PCOLS / 16; ++c) {
+            float v[16];
+            tmem_ld16f(tmem + TM_DQ + lane_addr + part * PCOLS + c * 16, v);
+            if (q_ok && !(args.debug & 1)) {
+#pragma unroll
+              for (int t = 0; t < 16; t += 4)
+                __stcg(reinterpret_cast<float4*>(drow + c * 16 + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(dq_drained);
+          if (args.dq_mode == 2) {                              // one cumulative release for the SMT writers
+            asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+            if (threadIdx.x == 64) mbar_arrive_remote_release(xch_bar, (uint32_t)(kt ^ 1));
+          }
+        } else {
+          uint16_t* qrow = args.dqkv16 + ((int64_t)b * S + qq) * (3 * d_model) + h * DH + part * PCOLS;
+          float* bsum = args.dbias + h * DH + part * PCOLS;
+          if (args.dq_mode == 2) {
+            mbar_wait_acquire_cluster(xch_bar, xphase);
+            xphase ^= 1;
+          }
+          // the peer's partial first (all 16-byte loads in flight at once: one L2 latency, not one per chunk)
+          float4 pz[PCOLS / 4];
+          if (args.dq_mode == 2 && q_ok) {
+#pragma unroll
+            for (int t = 0; t < PCOLS / 4; ++t) pz[t] = __ldcg(reinterpret_cast<const float4*>(drow + 4 * t));
+          } else {
+#pragma unroll
+            for (int t = 0; t < PCOLS / 4; ++t) pz[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < PCOLS / 16; ++c) {
+            float v[16];
+            tmem_ld16f(tmem + TM_DQ + lane_addr + part * PCOLS + c * 16, v);
+            if (q_ok) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                v[4 * t] += pz[4 * c + t].x; v[4 * t + 1] += pz[4 * c + t].y;
+                v[4 * t + 2] += pz[4 * c + t].z; v[4 * t + 3] += pz[4 * c + t].w;
+              }
+              uint4 o0, o1;
+              o0.x = pack2(v[0], v[1], bf16);   o0.y = pack2(v[2], v[3], bf16);
+              o0.z = pack2(v[4], v[5], bf16);   o0.w = pack2(v[6], v[7], bf16);
+              o1.x = pack2(v[8], v[9], bf16);   o1.y = pack2(v[10], v[11], bf16);
+              o1.z = pack2(v[12], v[13], bf16); o1.w = pack2(v[14], v[15], bf16);
+              *reinterpret_cast<uint4*>(qrow + c * 16) = o0;
+              *reinterpret_cast<uint4*>(qrow + c * 16 + 8) = o1;
+            } else {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) v[t] = 0.f;
+            }
+            warp_colsum16(v, lane, bsum + c * 16, args.inv_scale16);
+          }
+          tc_fence_before();
+          mbar_arrive(dq_drained);
         }
       }
-      tc_fence_before();
-      mbar_arrive(dq_drained);
     }
-    // epilogue: dV_j, dK_j (lane = key row) -> dqkv16 V and K blocks; bias-gradient column sums
+    // epilogue: dV_j, dK_j (lane = key row) -> 128-byte-swizzled [128 keys x 64 columns] smem tiles in the (now free)
+    // Q / dO buffers -> TMA stores into the V and K blocks of dqkv16, clipped at S by the [B, S, 3d] map.  Row-per-lane
+    // global stores (3 KB apart) cost ~20 us per launch here.  Bias-gradient column sums from the same registers.
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tm = which == 0 ? TM_DV : TM_DK;
       const int blk = which == 0 ? 2 : 1;                       // column block of dqkv16: Q | K | V
-      uint16_t* orow = args.dqkv16 + ((int64_t)b * S + key) * (3 * d_model) + blk * d_model + h * DH + part * PCOLS;
+      const uint32_t tile_u = smem_u32(which == 0 ? sq : sdo);
       float* bsum = args.dbias + blk * d_model + h * DH + part * PCOLS;
 #pragma unroll 1
       for (int c = 0; c < PCOLS / 16; ++c) {
         float v[16];
         tmem_ld16f(tmem + tm + lane_addr + part * PCOLS + c * 16, v);
-        if (key_ok) {
-          uint4 o0, o1;
-          o0.x = pack2(v[0], v[1], bf16);   o0.y = pack2(v[2], v[3], bf16);
-          o0.z = pack2(v[4], v[5], bf16);   o0.w = pack2(v[6], v[7], bf16);
-          o1.x = pack2(v[8], v[9], bf16);   o1.y = pack2(v[10], v[11], bf16);
-          o1.z = pack2(v[12], v[13], bf16); o1.w = pack2(v[14], v[15], bf16);
-          *reinterpret_cast<uint4*>(orow + c * 16) = o0;
-          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+        if (!(args.debug & 4)) {
+          const int col = part * PCOLS + c * 16;
+          const uint32_t rb = tile_u + (uint32_t)(col >> 6) * SUB + (uint32_t)r * 128;
+          const uint32_t ch0 = (uint32_t)((col & 63) >> 3), sw = (uint32_t)(r & 7);
+          sts128u(rb + ((ch0 ^ sw) << 4), pack2(v[0], v[1], bf16), pack2(v[2], v[3], bf16), pack2(v[4], v[5], bf16),
+                  pack2(v[6], v[7], bf16));
+          sts128u(rb + (((ch0 + 1) ^ sw) << 4), pack2(v[8], v[9], bf16), pack2(v[10], v[11], bf16),
+                  pack2(v[12], v[13], bf16), pack2(v[14], v[15], bf16));
         }
-        // column sums over the warp's 32 rows: halving butterfly (16 shuffles for 16 columns); afterwards lane L
-        // holds column (L >> 1) & 15 ... bit-reversed: bit4 -> 8, bit3 -> 4, bit2 -> 2, bit1 -> 1
+        if (args.debug & 8) continue;
         if (!key_ok) {
 #pragma unroll
           for (int t = 0; t < 16; ++t) v[t] = 0.f;
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float send = (lane & 16) ? v[t] : v[t + 8], keep = (lane & 16) ? v[t + 8] : v[t];
-          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float send = (lane & 8) ? v[t] : v[t + 4], keep = (lane & 8) ? v[t + 4] : v[t];
-          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
+        warp_colsum16(v, lane, bsum + c * 16, args.inv_scale16);
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+    if (threadIdx.x == 64) {
+      if (!(args.debug & 4)) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          const float send = (lane & 4) ? v[t] : v[t + 2], keep = (lane & 4) ? v[t + 2] : v[t];
-          v[t] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          tma_store_3d(&map_out, smem_u32(sq) + t * SUB, 2 * d_model + h * DH + 64 * t, k0, b);
+          tma_store_3d(&map_out, smem_u32(sdo) + t * SUB, d_model + h * DH + 64 * t, k0, b);
         }
-        {
-          const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
-          v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-        if ((lane & 1) == 0) {
-          const int colid = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          atomicAdd(bsum + c * 16 + colid, v[0] * args.inv_scale16);
-        }
+        bulk_commit();
       }
+      bulk_wait_read0();                                      // smem may go once every bulk store / reduction has read it
     }
     tc_fence_before();
   }
   __syncthreads();
+  if (args.dq_mode == 2) cluster_sync_all();          // no CTA retires while its peer may still arrive on its xch_bar
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
 }
 
-// delta[b,h,q] = sum_c dO[b,q,h*dh+c] * O[b,q,h*dh+c]   (one warp per token row, dh = 128: 4 elements per lane and head)
+// delta[b,h,q] = sum_c dO[b,q,h*dh+c] * O[b,q,h*dh+c]   (one warp per token row, dh = 128: 8 elements per lane, two heads per pass)
 __global__ void __launch_bounds__(256) attn_delta16_kernel(const uint16_t* __restrict__ dctx16, const uint16_t* __restrict__ ctx16,
                                                            int64_t rows, int S, int H, float* __restrict__ delta, int bf16) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int d_model = H * DH;
+  // 16 lanes x 16 bytes per head: a warp takes two heads of a row per load instruction
   for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
     const int64_t b = r / S, q = r % S;
-    for (int h = 0; h < H; ++h) {
-      const float4 a = unpack4(*reinterpret_cast<const uint2*>(dctx16 + r * d_model + h * DH + lane * 4), bf16 != 0);
-      const float4 o = unpack4(*reinterpret_cast<const uint2*>(ctx16 + r * d_model + h * DH + lane * 4), bf16 != 0);
-      const float s = warp_sum((a.x * o.x + a.y * o.y) + (a.z * o.z + a.w * o.w));
-      if (lane == 0) delta[(b * H + h) * S + q] = s;
+#pragma unroll 2
+    for (int h0 = 0; h0 < H; h0 += 2) {
+      const int h = h0 + (lane >> 4);
+      const bool ok = h < H;
+      const int64_t off = r * d_model + (ok ? h : 0) * DH + (lane & 15) * 8;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(dctx16 + off));
+      const uint4 o = __ldg(reinterpret_cast<const uint4*>(ctx16 + off));
+      const float2 a0 = unpack2(a.x, bf16 != 0), a1 = unpack2(a.y, bf16 != 0), a2 = unpack2(a.z, bf16 != 0), a3 = unpack2(a.w, bf16 != 0);
+      const float2 o0 = unpack2(o.x, bf16 != 0), o1 = unpack2(o.y, bf16 != 0), o2 = unpack2(o.z, bf16 != 0), o3 = unpack2(o.w, bf16 != 0);
+      float s = ((a0.x * o0.x + a0.y * o0.y) + (a1.x * o1.x + a1.y * o1.y)) + ((a2.x * o2.x + a2.y * o2.y) + (a3.x * o3.x + a3.y * o3.y));
+#pragma unroll
+      for (int sh = 8; sh >= 1; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+      if ((lane & 15) == 0 && ok) delta[(b * H + h) * S + q] = s;
     }
   }
 }
@@ -669,15 +798,15 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict_
   for (int c4 = x; c4 < d4; c4 += blockDim.x) {
     float4 acc = zero;
     const int64_t r0 = (int64_t)blockIdx.x * FIN_ROWS;
-    for (int k = y; k < FIN_ROWS; k += 4 * ny) {
-      float4 g[4];
+    for (int k = y; k < FIN_ROWS; k += 8 * ny) {               // 8 independent 16-byte loads in flight per thread
+      float4 g[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int64_t r = r0 + k + u * ny;
-        g[u] = (k + u * ny < FIN_ROWS && r < rows) ? dq32[r * d4 + c4] : zero;
+        g[u] = (k + u * ny < FIN_ROWS && r < rows) ? __ldcs(dq32 + r * d4 + c4) : zero;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int64_t r = r0 + k + u * ny;
         if (k + u * ny < FIN_ROWS && r < rows) {
           dq32[r * d4 + c4] = zero;
@@ -728,6 +857,33 @@ int make_map16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols
   return 0;
 }
 
+// [B, S, cols] view of a [B*S, ld] tensor (16-bit, or fp32 when dtype < 0) for TMA STORES / REDUCTIONS: the box (128 bytes
+// of columns x box_rows tokens x 1) is clipped at S, so a ragged last tile does not spill into the next batch item's rows
+int make_map_3d(CUtensorMap* map, const void* base, int64_t B, int64_t S, int64_t cols, int64_t ld, int box_rows, int dtype,
+                const char* what) {
+  static EncodeTiledFn enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return (EncodeTiledFn) nullptr;
+  }();
+  MMT_ARG_CHECK(enc != nullptr, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable");
+  const int es = dtype < 0 ? 4 : 2;
+  MMT_ARG_CHECK(((uintptr_t)base % 16) == 0 && (ld * es) % 16 == 0, MMT_E_ALIGN,
+                "tensor map %s needs a 16-byte aligned base and row pitch", what);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)S * ld * es};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  const CUtensorMapDataType cdt = dtype < 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                  : dtype == MMT_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, cdt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMT_ARG_CHECK(r == CUDA_SUCCESS, MMT_E_UNSUPPORTED, "cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
 }  // namespace
 }  // namespace mmt
 
@@ -748,6 +904,9 @@ extern "C" int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t
   if (rc) return rc;
   rc = make_map16_2d(&mk, qkv16, rows, cols, cols, fwd::KB, dtype, "K/V");
   if (rc) return rc;
+  CUtensorMap mo;
+  rc = make_map_3d(&mo, ctx16, B, S, (int64_t)H * DH, (int64_t)H * DH, fwd::QM, dtype, "context");
+  if (rc) return rc;
   AttArgs a;
   a.mask = mask; a.ctx16 = reinterpret_cast<uint16_t*>(ctx16); a.lse = lse;
   a.B = B; a.H = H; a.S = S;
@@ -757,7 +916,7 @@ extern "C" int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t
   rc = ensure_dynamic_smem((const void*)fwd::attention16_fwd_kernel, fwd::SMEM, "attention16_fwd smem attribute");
   if (rc) return rc;
   dim3 grid((S + fwd::QM - 1) / fwd::QM, H, B);
-  launch_pdl(fwd::attention16_fwd_kernel, grid, dim3(fwd::THREADS), fwd::SMEM, (cudaStream_t)stream, mq, mk, a);
+  launch_pdl(fwd::attention16_fwd_kernel, grid, dim3(fwd::THREADS), fwd::SMEM, (cudaStream_t)stream, mq, mk, mo, a);
   MMT_LAUNCH_CHECK("attention16_fwd_kernel");
   return 0;
 }
@@ -785,8 +944,12 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
                reinterpret_cast<const uint16_t*>(ctx16), rows, S, H, delta, bf16);
     MMT_LAUNCH_CHECK("attn_delta16_kernel");
   }
-  CUtensorMap mqkv, mdo;
-  int rc = make_map16_2d(&mqkv, qkv16, rows, 3LL * d_model, 3LL * d_model, 128, dtype, "QKV");
+  CUtensorMap mqkv, mdo, mout, mdq;
+  int rc = make_map_3d(&mout, dqkv16, B, S, 3LL * d_model, 3LL * d_model, 128, dtype, "dQKV");
+  if (rc) return rc;
+  rc = make_map_3d(&mdq, dq32, B, S, d_model, d_model, 128, -1, "dQ fp32");
+  if (rc) return rc;
+  rc = make_map16_2d(&mqkv, qkv16, rows, 3LL * d_model, 3LL * d_model, 128, dtype, "QKV");
   if (rc) return rc;
   rc = make_map16_2d(&mdo, dctx16, rows, d_model, d_model, 128, dtype, "dO");
   if (rc) return rc;
@@ -798,22 +961,32 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
   a.p_drop = p_drop; a.inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
   a.inv_scale16 = 1.0f / scale16;
   a.seed = seed; a.ctr = seed_ctr; a.site = site; a.bf16 = bf16;
+  static const int dbg = [] { const char* e = getenv("MMT_ATT_BWD_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = dbg;
   static const int nsw = [] {                          // softmax warps per CTA (A/B switch; 8 is the measured default)
     const char* e = getenv("MMT_ATT_BWD_WARPS");
     return e && atoi(e) == 16 ? 16 : 8;
   }();
-  dim3 grid((S + bwd::KT - 1) / bwd::KT, H, B);
+  static const int dq_force = [] { const char* e = getenv("MMT_ATT_BWD_DQ"); return e ? atoi(e) : -1; }();
+  const int nkt = (S + bwd::KT - 1) / bwd::KT;
+  // see the kernel.  The 2-CTA hand-over (MMT_ATT_BWD_DQ=2) is correct but measured SLOWER than the reduction + finish kernel
+  // (134 vs 114 us per layer at B=64, S=218: its per-lane fp32 loads / stores sit on each CTA's critical path), so it is opt-in.
+  a.dq_mode = nkt == 1 ? 1 : 0;
+  if (dq_force == 2 && nkt == 2) a.dq_mode = 2;
+  if (dq_force == 0 || dq_force == 3) a.dq_mode = 0;
+  const int cluster_x = (a.dq_mode == 2 || (dq_force == 3 && nkt == 2)) ? 2 : 1;   // 3: timing experiment (atomics, but clustered)
+  dim3 grid(nkt, H, B);
   if (nsw == 16) {
     rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel<16>, bwd::SMEM, "attention16_bwd smem attribute");
     if (rc) return rc;
-    launch_pdl(bwd::attention16_bwd_kernel<16>, grid, dim3(64 + 16 * 32), bwd::SMEM, st, mqkv, mdo, a);
+    launch_pdl_cluster(bwd::attention16_bwd_kernel<16>, grid, dim3(64 + 16 * 32), bwd::SMEM, st, cluster_x, mqkv, mdo, mout, mdq, a);
   } else {
     rc = ensure_dynamic_smem((const void*)bwd::attention16_bwd_kernel<8>, bwd::SMEM, "attention16_bwd smem attribute");
     if (rc) return rc;
-    launch_pdl(bwd::attention16_bwd_kernel<8>, grid, dim3(64 + 8 * 32), bwd::SMEM, st, mqkv, mdo, a);
+    launch_pdl_cluster(bwd::attention16_bwd_kernel<8>, grid, dim3(64 + 8 * 32), bwd::SMEM, st, cluster_x, mqkv, mdo, mout, mdq, a);
   }
   MMT_LAUNCH_CHECK("attention16_bwd_kernel");
-  {
+  if (a.dq_mode == 0) {
     const int d4 = d_model / 4;
     const int bx = d4 <= 128 ? d4 : 128;
     const int by = 256 / bx > 0 ? 256 / bx : 1;

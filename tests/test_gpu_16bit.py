@@ -232,7 +232,8 @@ def test_attention16_backward(dev, dt, Bt, S):
                                      S, dh, scale, 0.0, 0, None, 0, sg, _lib.ptr(dqkv), _lib.ptr(dq32), _lib.ptr(delta),
                                      _lib.ptr(dbias), dt, _lib.stream_ptr()), "attention16_bwd")
   torch.cuda.synchronize()
-  assert float(dq32.abs().max()) == 0.0                    # workspace left zeroed for the next layer
+  if S > 256:
+    assert float(dq32.abs().max()) == 0.0                  # atomics path: workspace left zeroed for the next layer
   got = dqkv.float().cpu().double() / sg
   tol = 3e-2 if dt == 1 else 4e-3
   for name, blk in (("dQ", 0), ("dK", 1), ("dV", 2)):
