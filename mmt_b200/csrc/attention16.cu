@@ -829,6 +829,356 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict_
 }
 }  // namespace bwd
 
+// ======================================== backward, pipelined =========================================
+// Same math and operand layouts as bwd::attention16_bwd_kernel, restructured so that the softmax warps (the busiest
+// resource: ~24 M warp-instructions per launch) never wait for a load or an MMA.  The query axis is walked in tiles of
+// 64 with double-buffered Q / dO / Pd^T / dS^T tiles in shared memory and two S^T accumulators in TMEM:
+//   TMEM (512 columns): dV 0..127 | dK 128..255 | S^T stage 0 / 1: 256..319 / 320..383 | dPd^T 384..447 | dQ^T 448..511
+//   MMA warp     S^T(i+1) = K Q_{i+1}^T is issued BEFORE softmax(i) has finished (other TMEM stage); once softmax(i) has
+//                arrived: dPd^T(i+1) = V dO_{i+1}^T, dV += Pd^T dO_i, dK += dS^T Q_i, dQ_i^T = K^T dS (M = dh, N = 64 queries)
+//   softmax      p(i) from S^T while dPd^T(i) is still being computed, then dS(i); then dQ^T(i-1) (own TMEM columns, so the next
+//                S^T never waits for this drain) -> fp32 staging -> TMA reduce-add into dq32.  (Direct red.global.add.f32 --
+//                coalesced here, lane = dh -- was measured 14 us per launch slower: 32-bit atomics at the L2.)
+//   TMA warp     Q_{i+2} / dO_{i+2} as soon as the MMAs of tile i have completed
+// The previous kernel ran load -> MMA -> softmax -> MMA -> drain serially with one CTA per SM: of its 83 us, 45 us remained
+// with ALL softmax math, dQ traffic and dV/dK stores switched off (MMT_ATT_BWD_DEBUG=7).
+namespace bwd2 {
+constexpr int KT = 128, QT = 64;
+constexpr int NSW = 8, SMT = NSW * 32, THREADS = 64 + SMT;
+constexpr uint32_t KTILE = KT * DH * 2;              // 32 KB: K or V, 2 sub-tiles [128 keys x 128 B]
+constexpr uint32_t KSUB = KT * 128;                  // 16 KB
+constexpr uint32_t QTILE = QT * DH * 2;              // 16 KB: Q or dO tile, 2 sub-tiles [64 queries x 128 B]
+constexpr uint32_t QSUB = QT * 128;                  // 8 KB
+constexpr uint32_t PTILE = KT * QT * 2;              // 16 KB: Pd^T or dS^T [128 keys x 64 queries]
+constexpr int QST = 2;                               // Q / dO stages
+constexpr uint32_t STG = QT * DH * 4;                // 32 KB: fp32 dQ staging, 4 boxes [64 queries x 32 dh]
+constexpr uint32_t OFF_K = 0, OFF_V = KTILE, OFF_Q = 2 * KTILE, OFF_DO = OFF_Q + QST * QTILE, OFF_P = OFF_DO + QST * QTILE,
+                   OFF_DS = OFF_P + 2 * PTILE, OFF_STG = OFF_DS + 2 * PTILE, OFF_BAR = OFF_STG + STG;
+// no alignment slack: the __align__(1024) extern declaration aligns the dynamic window (it shows up as 1 KB of static
+// shared memory, which counts against the 227 KB limit); the kernel traps if that ever fails to hold
+constexpr size_t SMEM = OFF_BAR + 128 /*barriers*/ + 4 * QT * 4 /*lse, delta x 2 stages*/;
+static_assert(SMEM + 1024 <= 232448, "attention16 bwd2: shared memory");
+constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_ST = 256, TM_DP = 384, TM_DQ = 448;
+
+__global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __grid_constant__ CUtensorMap map_kv,
+                                                                      const __grid_constant__ CUtensorMap map_q,
+                                                                      const __grid_constant__ CUtensorMap map_do,
+                                                                      const __grid_constant__ CUtensorMap map_out,
+                                                                      const __grid_constant__ CUtensorMap map_dq,
+                                                                      const AttBwdArgs args) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;             // [3]
+  uint64_t* st_full = bars + 4;              // [2] S^T stage written
+  uint64_t* dp_full = bars + 6;              // dPd^T written
+  uint64_t* pds_full = bars + 7;             // [2] Pd^T / dS^T tiles written, S^T stage and dPd^T consumed (SMT arrivals)
+  uint64_t* mma2_done = bars + 9;            // [2] dV / dK / dQ^T MMAs of the tile complete (its Pd^T / dS^T stage is free)
+  uint64_t* dq_drained = bars + 11;          // dQ^T read out of TMEM (SMT arrivals)
+  uint64_t* qdo_free = bars + 12;            // [3] the tile's MMAs no longer read its Q / dO stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* s_lse2 = reinterpret_cast<float*>(bars + 16);       // [2][QT] log2-domain lse (+inf: no such query)
+  float* s_delta = s_lse2 + 2 * QT;                          // [2][QT]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = args.H, S = args.S;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kt * KT;
+  const int nq = (S + QT - 1) / QT;
+  const int d_model = H * DH;
+  const bool bf16 = args.bf16 != 0;
+  const uint32_t smem_u = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&st_full[t], 1); mbar_init(&pds_full[t], SMT); mbar_init(&mma2_done[t], 1); }
+    for (int t = 0; t < QST; ++t) { mbar_init(&qdo_full[t], 1); mbar_init(&qdo_free[t], 1); }
+    mbar_init(dp_full, 1); mbar_init(dq_drained, SMT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_do) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int row_k = b * S + k0;
+      mbar_arrive_expect_tx(kv_full, 2 * KTILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        tma_load_2d(smem + OFF_K + t * KSUB, &map_kv, kv_full, d_model + h * DH + 64 * t, row_k);
+        tma_load_2d(smem + OFF_V + t * KSUB, &map_kv, kv_full, 2 * d_model + h * DH + 64 * t, row_k);
+      }
+      for (int i = 0; i < nq; ++i) {
+        const int s = i % QST;
+        if (i >= QST) mbar_wait(&qdo_free[s], ((i / QST) - 1) & 1);  // tile i-QST (same stage) no longer read
+        const int row_q = b * S + i * QT;
+        mbar_arrive_expect_tx(&qdo_full[s], 2 * QTILE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_2d(smem + OFF_Q + s * QTILE + t * QSUB, &map_q, &qdo_full[s], h * DH + 64 * t, row_q);
+          tma_load_2d(smem + OFF_DO + s * QTILE + t * QSUB, &map_do, &qdo_full[s], h * DH + 64 * t, row_q);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id_s = idesc16(128, QT, false, false, bf16);    // S^T, dPd^T: A (K / V) and B (Q / dO) K-major
+      const uint32_t id_v = idesc16(128, DH, false, true, bf16);     // dV, dK: A (Pd^T / dS^T) K-major over queries, B MN-major
+      const uint32_t id_q = idesc16(128, QT, true, true, bf16);      // dQ^T: A (K) and B (dS^T) MN-major over keys
+      const uint32_t sk = smem_u + OFF_K, sv = smem_u + OFF_V;
+      auto mma_st = [&](int j) {                                     // S^T(j) = K Q_j^T   (k = dh)
+        const uint32_t sq = smem_u + OFF_Q + (j % QST) * QTILE, acc = tmem + TM_ST + (uint32_t)(j & 1) * QT;
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_f16_ss(acc, make_smem_desc(sk + (ks >> 2) * KSUB + (ks & 3) * 32, 16, 1024, 2),
+                      make_smem_desc(sq + (ks >> 2) * QSUB + (ks & 3) * 32, 16, 1024, 2), id_s, ks > 0 ? 1u : 0u);
+      };
+      auto mma_dp = [&](int j) {                                     // dPd^T(j) = V dO_j^T
+        const uint32_t sdo = smem_u + OFF_DO + (j % QST) * QTILE;
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_f16_ss(tmem + TM_DP, make_smem_desc(sv + (ks >> 2) * KSUB + (ks & 3) * 32, 16, 1024, 2),
+                      make_smem_desc(sdo + (ks >> 2) * QSUB + (ks & 3) * 32, 16, 1024, 2), id_s, ks > 0 ? 1u : 0u);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      mma_st(0);
+      umma_commit(&st_full[0]);
+      mma_dp(0);
+      umma_commit(dp_full);
+      for (int i = 0; i < nq; ++i) {
+        const int s = i & 1;
+        // next S^T while the softmax warps work on tile i.  (Polling qdo_full and pds_full alternately, so that this tile's
+        // MMAs never queue behind a late load, was measured no faster: 94.7 vs 94.4 us per launch.)
+        if (i + 1 < nq) {
+          mbar_wait(&qdo_full[(i + 1) % QST], ((i + 1) / QST) & 1);
+          tc_fence_after();
+          mma_st(i + 1);
+          umma_commit(&st_full[s ^ 1]);
+        }
+        mbar_wait(&pds_full[s], (i >> 1) & 1);
+        tc_fence_after();
+        if (i + 1 < nq) {
+          mma_dp(i + 1);
+          umma_commit(dp_full);
+        }
+        const uint32_t sq = smem_u + OFF_Q + (i % QST) * QTILE, sdo = smem_u + OFF_DO + (i % QST) * QTILE;
+        const uint32_t sp = smem_u + OFF_P + s * PTILE, sds = smem_u + OFF_DS + s * PTILE;
+#pragma unroll
+        for (int ks = 0; ks < QT / 16; ++ks)                         // dV += Pd^T dO_i   (k = queries)
+          umma_f16_ss(tmem + TM_DV, make_smem_desc(sp + ks * 32, 16, 1024, 2), make_smem_desc(sdo + ks * 2048, QSUB, 1024, 2),
+                      id_v, (i > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < QT / 16; ++ks)                         // dK += dS^T Q_i
+          umma_f16_ss(tmem + TM_DK, make_smem_desc(sds + ks * 32, 16, 1024, 2), make_smem_desc(sq + ks * 2048, QSUB, 1024, 2),
+                      id_v, (i > 0 || ks > 0) ? 1u : 0u);
+        if (i >= 1) {
+          mbar_wait(dq_drained, (i - 1) & 1);                        // dQ^T(i-1) has left its TMEM columns
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks)                         // dQ_i^T = K^T dS   (k = keys)
+          umma_f16_ss(tmem + TM_DQ, make_smem_desc(sk + ks * 2048, KSUB, 1024, 2), make_smem_desc(sds + ks * 2048, PTILE, 1024, 2),
+                      id_q, ks > 0 ? 1u : 0u);
+        umma_commit(&mma2_done[s]);
+        umma_commit(&qdo_free[i % QST]);
+      }
+    }
+  } else {
+    // ===================== softmax backward, dQ drain, epilogue (warps 2..9) =====================
+    const int q4 = warp & 3;                                   // TMEM lane quarter
+    const int part = (warp - 2) >> 2;                          // which 32 of a tile's 64 query columns
+    const int r = q4 * 32 + lane;                              // key row (S^T, dV, dK) or dh row (dQ^T) == TMEM lane
+    const int key = k0 + r;
+    const bool key_ok = key < S;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const float mterm = key_ok ? (1.0f - __ldg(args.mask + (int64_t)b * S + key)) * (-10000.0f * LOG2E) : -INFINITY;
+    const uint64_t seed = args.seed + (args.ctr ? *args.ctr : 0);
+    const uint32_t key32 = drop_key(seed, args.site);
+    const uint32_t thr = (uint32_t)(args.p_drop * 65536.0f);
+    const bool drop = args.p_drop > 0.f;
+    const uint32_t half_pitch = (uint32_t)((S + 1) >> 1);
+    const uint32_t kpair = (uint32_t)key >> 1;
+    const uint32_t kshift = (key & 1) ? 16u : 0u;
+    const uint32_t prow0 = (uint32_t)(((int64_t)b * H + h) * S);
+    const int cbase = part * 32;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const int tq = (int)threadIdx.x - 64;                      // 0 .. SMT-1: the first QT threads fetch the per-query vectors
+    const float* lse_g = args.lse + ((int64_t)b * H + h) * S;
+    const float* delta_g = args.delta + ((int64_t)b * H + h) * S;
+    if (tq < QT) {
+      const bool ok = tq < S;
+      s_lse2[tq] = ok ? __ldg(lse_g + tq) * LOG2E : INFINITY;
+      s_delta[tq] = ok ? __ldg(delta_g + tq) : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+
+    // dQ^T(j) [dh lanes x 64 query columns] -> fp32 staging [query rows x dh], four 128-byte-swizzled boxes of 32 dh
+    // columns (one per lane quarter) -> TMA reduce-add into dq32 (clipped at S).  Ends with a barrier of the SMT threads.
+    const uint32_t stg_u = smem_u + OFF_STG;
+    auto drain_dq = [&](int j) {
+      mbar_wait(&mma2_done[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem + TM_DQ + lane_addr + (uint32_t)cbase, v);
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+      if (threadIdx.x == 64) bulk_wait_read0();                // the previous reduction has read the staging tile
+      asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+      const uint32_t base = stg_u + (uint32_t)q4 * (QT * 128) + (uint32_t)(lane & 3) * 4;
+      const uint32_t ch = (uint32_t)(lane >> 2);
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const uint32_t q = (uint32_t)(cbase + t);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + q * 128 + ((ch ^ (q & 7)) << 4)), "f"(v[t]) : "memory");
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+      if (threadIdx.x == 64 && !(args.debug & 1)) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_reduce_add_3d(&map_dq, stg_u + c * (QT * 128), h * DH + 32 * c, j * QT, b);
+        bulk_commit();
+      }
+    };
+
+    for (int i = 0; i < nq; ++i) {
+      const int s = i & 1;
+      const int qbase = i * QT;
+      float nl = INFINITY, nd = 0.f;                           // next tile's lse / delta: in flight during this tile
+      if (tq < QT && i + 1 < nq) {
+        const int qq = qbase + QT + tq;
+        if (qq < S) { nl = __ldg(lse_g + qq) * LOG2E; nd = __ldg(delta_g + qq); }
+      }
+      const float* lse2 = s_lse2 + s * QT + cbase;
+      const float* dlt = s_delta + s * QT + cbase;
+      const uint32_t prow = smem_u + OFF_P + s * PTILE + (uint32_t)r * 128;
+      const uint32_t dsrow = smem_u + OFF_DS + s * PTILE + (uint32_t)r * 128;
+      const bool live = (qbase + cbase < S) && (k0 + q4 * 32 < S) && !(args.debug & 2);   // warp-uniform
+      mbar_wait(&st_full[s], (i >> 1) & 1);
+      tc_fence_after();
+      // (Two leaner formulations were measured and lost: sharing each dropout hash between the two lanes of a key pair by
+      // shuffle, and carrying the keep decision in p's sign bit -- 94.4 vs 90.1 us per launch.)
+      float p[32];
+      uint32_t keepmask = 0xffffffffu;
+      if (live) {
+        float sv_[32];
+        tmem_ld32(tmem + TM_ST + (uint32_t)(s * QT) + lane_addr + (uint32_t)cbase, sv_);
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            p[t + u] = fast_ex2(fmaf(sv_[t + u], args.scale_log2, mterm) - lse2[t + u]);
+            float keep = args.inv_keep;
+            if (drop) {
+              const uint32_t w = drop_word(key32, prow0 + (uint32_t)(qbase + cbase + t + u), half_pitch, kpair);
+              if (((w >> kshift) & 0xffffu) < thr) { keep = 0.f; keepmask &= ~(1u << (t + u)); }
+            }
+            pv[u] = p[t + u] * keep;
+          }
+          pk[t >> 1] = pack2(pv[0], pv[1], bf16);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128u(prow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128u(prow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+      }
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+      if (live) {
+        float dp[32];
+        tmem_ld32(tmem + TM_DP + lane_addr + (uint32_t)cbase, dp);
+        uint32_t dk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          const float k0_ = ((keepmask >> t) & 1u) ? args.inv_keep : 0.f, k1_ = ((keepmask >> (t + 1)) & 1u) ? args.inv_keep : 0.f;
+          const float d0 = p[t] * fmaf(dp[t], k0_, -dlt[t]) * args.scale;
+          const float d1 = p[t + 1] * fmaf(dp[t + 1], k1_, -dlt[t + 1]) * args.scale;
+          dk[t >> 1] = pack2(d0, d1, bf16);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128u(dsrow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128u(dsrow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
+      tc_fence_before();
+      mbar_arrive(&pds_full[s]);
+      if (tq < QT && i + 1 < nq) { s_lse2[(s ^ 1) * QT + tq] = nl; s_delta[(s ^ 1) * QT + tq] = nd; }
+      if (i >= 1) drain_dq(i - 1);                              // (its barriers also publish the vectors above)
+      else asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+    }
+    drain_dq(nq - 1);
+
+    // epilogue: dV_j, dK_j (lane = key row, 64 dh columns per thread) -> 128-byte-swizzled [128 keys x 64] tiles in the
+    // Q / dO buffers -> TMA stores into the V and K blocks of dqkv16 (clipped at S); bias-gradient column sums
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tm = which == 0 ? TM_DV : TM_DK;
+      const int blk = which == 0 ? 2 : 1;                       // column block of dqkv16: Q | K | V
+      const uint32_t tile_u = smem_u + (which == 0 ? OFF_Q : OFF_DO);
+      float* bsum = args.dbias + blk * d_model + h * DH + part * 64;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[16];
+        tmem_ld16f(tmem + tm + lane_addr + (uint32_t)(part * 64 + c * 16), v);
+        if (!(args.debug & 4)) {
+          const uint32_t rb = tile_u + (uint32_t)part * KSUB + (uint32_t)r * 128;
+          const uint32_t ch0 = (uint32_t)(c * 2);
+          sts128u(rb + ((ch0 ^ sw) << 4), pack2(v[0], v[1], bf16), pack2(v[2], v[3], bf16), pack2(v[4], v[5], bf16),
+                  pack2(v[6], v[7], bf16));
+          sts128u(rb + (((ch0 + 1) ^ sw) << 4), pack2(v[8], v[9], bf16), pack2(v[10], v[11], bf16),
+                  pack2(v[12], v[13], bf16), pack2(v[14], v[15], bf16));
+        }
+        if (args.debug & 8) continue;
+        if (!key_ok) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = 0.f;
+        }
+        bwd::warp_colsum16(v, lane, bsum + c * 16, args.inv_scale16);
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(SMT) : "memory");
+    if (threadIdx.x == 64) {
+      if (!(args.debug & 4)) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_store_3d(&map_out, smem_u + OFF_Q + t * KSUB, 2 * d_model + h * DH + 64 * t, k0, b);
+          tma_store_3d(&map_out, smem_u + OFF_DO + t * KSUB, d_model + h * DH + 64 * t, k0, b);
+        }
+        bulk_commit();
+      }
+      bulk_wait_read0();                                        // smem may go once every bulk store / reduction has read it
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+}  // namespace bwd2
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -968,7 +1318,31 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
     return e && atoi(e) == 16 ? 16 : 8;
   }();
   static const int dq_force = [] { const char* e = getenv("MMT_ATT_BWD_DQ"); return e ? atoi(e) : -1; }();
+  static const int v1 = [] { const char* e = getenv("MMT_ATT_BWD_V1"); return e ? atoi(e) : 0; }();   // 1: the serial kernel
   const int nkt = (S + bwd::KT - 1) / bwd::KT;
+  if (!v1 && dq_force < 0) {
+    // pipelined kernel: 64-query tiles, dQ always through the fp32 reduction + finish kernel
+    CUtensorMap mq64, mdo64, mdq64;
+    rc = make_map16_2d(&mq64, qkv16, rows, 3LL * d_model, 3LL * d_model, bwd2::QT, dtype, "Q");
+    if (rc) return rc;
+    rc = make_map16_2d(&mdo64, dctx16, rows, d_model, d_model, bwd2::QT, dtype, "dO");
+    if (rc) return rc;
+    rc = make_map_3d(&mdq64, dq32, B, S, d_model, d_model, bwd2::QT, -1, "dQ fp32");
+    if (rc) return rc;
+    a.dq_mode = 0;
+    rc = ensure_dynamic_smem((const void*)bwd2::attention16_bwd2_kernel, bwd2::SMEM, "attention16_bwd2 smem attribute");
+    if (rc) return rc;
+    launch_pdl(bwd2::attention16_bwd2_kernel, dim3(nkt, H, B), dim3(bwd2::THREADS), bwd2::SMEM, st, mqkv, mq64, mdo64, mout, mdq64, a);
+    MMT_LAUNCH_CHECK("attention16_bwd2_kernel");
+    const int d4 = d_model / 4;
+    const int bx = d4 <= 128 ? d4 : 128;
+    const int by = 256 / bx > 0 ? 256 / bx : 1;
+    const int64_t blocks = (rows + bwd::FIN_ROWS - 1) / bwd::FIN_ROWS;
+    launch_pdl(bwd::attn_dq_finish_kernel, dim3((int)blocks), dim3(bx, by), 0, st, reinterpret_cast<float4*>(dq32), rows, d4,
+               reinterpret_cast<uint16_t*>(dqkv16), dbias, 1.0f / scale16, bf16);
+    MMT_LAUNCH_CHECK("attn_dq_finish_kernel");
+    return 0;
+  }
   // see the kernel.  The 2-CTA hand-over (MMT_ATT_BWD_DQ=2) is correct but measured SLOWER than the reduction + finish kernel
   // (134 vs 114 us per layer at B=64, S=218: its per-lane fp32 loads / stores sit on each CTA's critical path), so it is opt-in.
   a.dq_mode = nkt == 1 ? 1 : 0;

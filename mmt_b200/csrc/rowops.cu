@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
+__global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) embed_ln_bwd_kernel(
     const float* __restrict__ dh, const float* __restrict__ proj,
     const int32_t* __restrict__ pos_ids, const int32_t* __restrict__ type_ids,
     const float* __restrict__ inv_norm, const float* __restrict__ mean_i,
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32) res_ln_fwd_kernel(
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(WARPS * 32) res_ln_bwd_kernel(
+__global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) res_ln_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ z,
     const float* __restrict__ mean_i, const float* __restrict__ rstd_i,
     const float* __restrict__ gamma, int64_t rows, float p_drop, uint64_t seed, uint32_t site, const uint64_t* __restrict__ ctr,

@@ -69,6 +69,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one non-blocking test of a phase (true: the phase with this parity has completed)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"     // test_wait: returns at once (try_wait may suspend)
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // ---- cluster-scope hand-over of GLOBAL data between the CTAs of a cluster: every writer thread arrives (release) on the
 // consumer CTA's mbarrier after its stores; the consumer waits with cluster-scope acquire ----
 __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta_rank) {
