@@ -354,10 +354,11 @@ int mmt_ln16_bwd(const float* dy, const float* dy2, const float* z, const float*
 
 /* Fused self-attention (model/bert.py:136-172) on 16-bit operands, nothing of size S x S in HBM:
  * forward  ctx16[b,i,h*dh:(h+1)*dh] = dropout(softmax(Q K^T * scale + (1-mask) * -10000)) V, lse [B,H,S];
- * backward recomputes the probabilities from qkv16 and lse (the Philox mask from (seed, site)) and writes
+ * backward recomputes the probabilities from qkv16 and lse (the dropout decisions from (seed, site)) and writes
  *          dqkv16 = scale16-domain gradients of Q | K | V (same layout as qkv16), accumulating the QKV bias
  *          gradient dbias [3*H*dh] (fp32, divided by scale16).  dctx16 carries scale16 already.
- * dh must be 128, d = H*dh.  dq32 is a zeroed fp32 workspace [B*S, H*dh] the kernel accumulates dQ in. */
+ * dh must be 128, d = H*dh.  dq32 is a zeroed fp32 workspace [B*S, H*dh] the key-tile CTAs reduce dQ into (TMA
+ * reduce-add); the call leaves it zeroed again.  delta [B,H,S] is scratch (dO . O per query). */
 int mmt_attention16_fwd(const void* qkv16, const float* mask, int32_t B, int32_t H, int32_t S, int32_t dh,
                         float scale, float p_drop, uint64_t seed, const uint64_t* seed_ctr, uint32_t site,
                         void* ctx16, float* lse, int32_t dtype, void* stream);

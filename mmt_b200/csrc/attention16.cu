@@ -829,6 +829,10 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict_
 }
 }  // namespace bwd
 
+// N consecutive TMEM columns of this thread's lane (N = 16 or 32)
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16f(taddr, v); }
+
 // ======================================== backward, pipelined =========================================
 // Same math and operand layouts as bwd::attention16_bwd_kernel, restructured so that the softmax warps (the busiest
 // resource: ~24 M warp-instructions per launch) never wait for a load or an MMA.  The query axis is walked in tiles of
@@ -844,7 +848,7 @@ __global__ void __launch_bounds__(256) attn_dq_finish_kernel(float4* __restrict_
 // with ALL softmax math, dQ traffic and dV/dK stores switched off (MMT_ATT_BWD_DEBUG=7).
 namespace bwd2 {
 constexpr int KT = 128, QT = 64;
-constexpr int NSW = 8, SMT = NSW * 32, THREADS = 64 + SMT;
+// NSW softmax warps (8 or 16): PARTS = NSW / 4 warps share a TMEM lane quarter and split a tile's 64 query columns
 constexpr uint32_t KTILE = KT * DH * 2;              // 32 KB: K or V, 2 sub-tiles [128 keys x 128 B]
 constexpr uint32_t KSUB = KT * 128;                  // 16 KB
 constexpr uint32_t QTILE = QT * DH * 2;              // 16 KB: Q or dO tile, 2 sub-tiles [64 queries x 128 B]
@@ -860,12 +864,17 @@ constexpr size_t SMEM = OFF_BAR + 128 /*barriers*/ + 4 * QT * 4 /*lse, delta x 2
 static_assert(SMEM + 1024 <= 232448, "attention16 bwd2: shared memory");
 constexpr uint32_t TM_DV = 0, TM_DK = 128, TM_ST = 256, TM_DP = 384, TM_DQ = 448;
 
-__global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __grid_constant__ CUtensorMap map_kv,
+template <int NSW>
+__global__ void __launch_bounds__(64 + NSW * 32, 1) attention16_bwd2_kernel(const __grid_constant__ CUtensorMap map_kv,
                                                                       const __grid_constant__ CUtensorMap map_q,
                                                                       const __grid_constant__ CUtensorMap map_do,
                                                                       const __grid_constant__ CUtensorMap map_out,
                                                                       const __grid_constant__ CUtensorMap map_dq,
                                                                       const AttBwdArgs args) {
+  constexpr int SMT = NSW * 32;                       // softmax threads
+  constexpr int PARTS = NSW / 4;
+  constexpr int CW = QT / PARTS;                      // query columns of a tile per thread (32 or 16)
+  constexpr int EW = DH / PARTS;                      // dh columns of dV / dK per thread (64 or 32)
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -1000,7 +1009,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
   } else {
     // ===================== softmax backward, dQ drain, epilogue (warps 2..9) =====================
     const int q4 = warp & 3;                                   // TMEM lane quarter
-    const int part = (warp - 2) >> 2;                          // which 32 of a tile's 64 query columns
+    const int part = (warp - 2) >> 2;                          // which CW of a tile's 64 query columns
     const int r = q4 * 32 + lane;                              // key row (S^T, dV, dK) or dh row (dQ^T) == TMEM lane
     const int key = k0 + r;
     const bool key_ok = key < S;
@@ -1014,7 +1023,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
     const uint32_t kpair = (uint32_t)key >> 1;
     const uint32_t kshift = (key & 1) ? 16u : 0u;
     const uint32_t prow0 = (uint32_t)(((int64_t)b * H + h) * S);
-    const int cbase = part * 32;
+    const int cbase = part * CW;
     const uint32_t sw = (uint32_t)(r & 7);
     const int tq = (int)threadIdx.x - 64;                      // 0 .. SMT-1: the first QT threads fetch the per-query vectors
     const float* lse_g = args.lse + ((int64_t)b * H + h) * S;
@@ -1032,8 +1041,8 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
     auto drain_dq = [&](int j) {
       mbar_wait(&mma2_done[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem + TM_DQ + lane_addr + (uint32_t)cbase, v);
+      float v[CW];
+      tmem_ldn(tmem + TM_DQ + lane_addr + (uint32_t)cbase, v);
       tc_fence_before();
       mbar_arrive(dq_drained);
       if (threadIdx.x == 64) bulk_wait_read0();                // the previous reduction has read the staging tile
@@ -1041,7 +1050,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
       const uint32_t base = stg_u + (uint32_t)q4 * (QT * 128) + (uint32_t)(lane & 3) * 4;
       const uint32_t ch = (uint32_t)(lane >> 2);
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
+      for (int t = 0; t < CW; ++t) {
         const uint32_t q = (uint32_t)(cbase + t);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + q * 128 + ((ch ^ (q & 7)) << 4)), "f"(v[t]) : "memory");
       }
@@ -1071,14 +1080,14 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
       tc_fence_after();
       // (Two leaner formulations were measured and lost: sharing each dropout hash between the two lanes of a key pair by
       // shuffle, and carrying the keep decision in p's sign bit -- 94.4 vs 90.1 us per launch.)
-      float p[32];
+      float p[CW];
       uint32_t keepmask = 0xffffffffu;
       if (live) {
-        float sv_[32];
-        tmem_ld32(tmem + TM_ST + (uint32_t)(s * QT) + lane_addr + (uint32_t)cbase, sv_);
-        uint32_t pk[16];
+        float sv_[CW];
+        tmem_ldn(tmem + TM_ST + (uint32_t)(s * QT) + lane_addr + (uint32_t)cbase, sv_);
+        uint32_t pk[CW / 2];
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
+        for (int t = 0; t < CW; t += 2) {
           float pv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -1093,31 +1102,31 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
           pk[t >> 1] = pack2(pv[0], pv[1], bf16);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          sts128u(prow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < CW / 8; ++c)
+          sts128u(prow + ((((uint32_t)(part * (CW / 8) + c)) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sts128u(prow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+        for (int c = 0; c < CW / 8; ++c) sts128u(prow + ((((uint32_t)(part * (CW / 8) + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
       }
       mbar_wait(dp_full, i & 1);
       tc_fence_after();
       if (live) {
-        float dp[32];
-        tmem_ld32(tmem + TM_DP + lane_addr + (uint32_t)cbase, dp);
-        uint32_t dk[16];
+        float dp[CW];
+        tmem_ldn(tmem + TM_DP + lane_addr + (uint32_t)cbase, dp);
+        uint32_t dk[CW / 2];
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
+        for (int t = 0; t < CW; t += 2) {
           const float k0_ = ((keepmask >> t) & 1u) ? args.inv_keep : 0.f, k1_ = ((keepmask >> (t + 1)) & 1u) ? args.inv_keep : 0.f;
           const float d0 = p[t] * fmaf(dp[t], k0_, -dlt[t]) * args.scale;
           const float d1 = p[t + 1] * fmaf(dp[t + 1], k1_, -dlt[t + 1]) * args.scale;
           dk[t >> 1] = pack2(d0, d1, bf16);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          sts128u(dsrow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        for (int c = 0; c < CW / 8; ++c)
+          sts128u(dsrow + ((((uint32_t)(part * (CW / 8) + c)) ^ sw) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sts128u(dsrow + ((((uint32_t)(part * 4 + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
+        for (int c = 0; c < CW / 8; ++c) sts128u(dsrow + ((((uint32_t)(part * (CW / 8) + c)) ^ sw) << 4), 0u, 0u, 0u, 0u);
       }
       fence_proxy_async_smem();                                 // generic-proxy smem writes -> visible to the MMAs
       tc_fence_before();
@@ -1128,21 +1137,22 @@ __global__ void __launch_bounds__(THREADS, 1) attention16_bwd2_kernel(const __gr
     }
     drain_dq(nq - 1);
 
-    // epilogue: dV_j, dK_j (lane = key row, 64 dh columns per thread) -> 128-byte-swizzled [128 keys x 64] tiles in the
+    // epilogue: dV_j, dK_j (lane = key row, EW dh columns per thread) -> 128-byte-swizzled [128 keys x 64] tiles in the
     // Q / dO buffers -> TMA stores into the V and K blocks of dqkv16 (clipped at S); bias-gradient column sums
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const uint32_t tm = which == 0 ? TM_DV : TM_DK;
       const int blk = which == 0 ? 2 : 1;                       // column block of dqkv16: Q | K | V
       const uint32_t tile_u = smem_u + (which == 0 ? OFF_Q : OFF_DO);
-      float* bsum = args.dbias + blk * d_model + h * DH + part * 64;
+      float* bsum = args.dbias + blk * d_model + h * DH + part * EW;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < EW / 16; ++c) {
         float v[16];
-        tmem_ld16f(tmem + tm + lane_addr + (uint32_t)(part * 64 + c * 16), v);
+        const int col = part * EW + c * 16;
+        tmem_ld16f(tmem + tm + lane_addr + (uint32_t)col, v);
         if (!(args.debug & 4)) {
-          const uint32_t rb = tile_u + (uint32_t)part * KSUB + (uint32_t)r * 128;
-          const uint32_t ch0 = (uint32_t)(c * 2);
+          const uint32_t rb = tile_u + (uint32_t)(col >> 6) * KSUB + (uint32_t)r * 128;
+          const uint32_t ch0 = (uint32_t)((col & 63) >> 3);
           sts128u(rb + ((ch0 ^ sw) << 4), pack2(v[0], v[1], bf16), pack2(v[2], v[3], bf16), pack2(v[4], v[5], bf16),
                   pack2(v[6], v[7], bf16));
           sts128u(rb + (((ch0 + 1) ^ sw) << 4), pack2(v[8], v[9], bf16), pack2(v[10], v[11], bf16),
@@ -1330,9 +1340,17 @@ extern "C" int mmt_attention16_bwd(const void* qkv16, const void* ctx16, const v
     rc = make_map_3d(&mdq64, dq32, B, S, d_model, d_model, bwd2::QT, -1, "dQ fp32");
     if (rc) return rc;
     a.dq_mode = 0;
-    rc = ensure_dynamic_smem((const void*)bwd2::attention16_bwd2_kernel, bwd2::SMEM, "attention16_bwd2 smem attribute");
-    if (rc) return rc;
-    launch_pdl(bwd2::attention16_bwd2_kernel, dim3(nkt, H, B), dim3(bwd2::THREADS), bwd2::SMEM, st, mqkv, mq64, mdo64, mout, mdq64, a);
+    if (nsw == 16) {
+      rc = ensure_dynamic_smem((const void*)bwd2::attention16_bwd2_kernel<16>, bwd2::SMEM, "attention16_bwd2 smem attribute");
+      if (rc) return rc;
+      launch_pdl(bwd2::attention16_bwd2_kernel<16>, dim3(nkt, H, B), dim3(64 + 16 * 32), bwd2::SMEM, st, mqkv, mq64, mdo64, mout,
+                 mdq64, a);
+    } else {
+      rc = ensure_dynamic_smem((const void*)bwd2::attention16_bwd2_kernel<8>, bwd2::SMEM, "attention16_bwd2 smem attribute");
+      if (rc) return rc;
+      launch_pdl(bwd2::attention16_bwd2_kernel<8>, dim3(nkt, H, B), dim3(64 + 8 * 32), bwd2::SMEM, st, mqkv, mq64, mdo64, mout,
+                 mdq64, a);
+    }
     MMT_LAUNCH_CHECK("attention16_bwd2_kernel");
     const int d4 = d_model / 4;
     const int bx = d4 <= 128 ? d4 : 128;
