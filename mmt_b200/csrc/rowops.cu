@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32) embed_ln_fwd_kernel(
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) embed_ln_bwd_kernel(
+__global__ void __launch_bounds__(WARPS * 32) embed_ln_bwd_kernel(
     const float* __restrict__ dh, const float* __restrict__ proj,
     const int32_t* __restrict__ pos_ids, const int32_t* __restrict__ type_ids,
     const float* __restrict__ inv_norm, const float* __restrict__ mean_i,
@@ -115,8 +115,20 @@ __global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) embed_ln_bwd_ker
   load_row<VEC>(gamma, lane, g);
 #pragma unroll
   for (int i = 0; i < VEC; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
-    const int s = (int)(r % S), b = (int)(r / S);
+  // Rows are walked position-major (j = s * B + b) in one contiguous chunk per warp: consecutive rows then share the token
+  // type and -- with regular frame sampling -- the position id, so their embedding gradients are summed in registers and
+  // flushed once per run.  (One pair of 512-float atomic rows per TOKEN was 3.6 M float4 atomics on 51 table rows.)
+  const int64_t warps_total = (int64_t)gridDim.x * WARPS;
+  const int64_t chunk = (rows + warps_total - 1) / warps_total;
+  const int64_t j0 = ((int64_t)blockIdx.x * WARPS + warp) * chunk;
+  const int64_t j1 = j0 + chunk < rows ? j0 + chunk : rows;
+  int cur_pos = -1, cur_type = -1;
+  float4 accp[VEC], acct[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) accp[i] = acct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t j = j0; j < j1; ++j) {
+    const int s = (int)(j / B), b = (int)(j % B);
+    const int64_t r = (int64_t)b * S + s;
     // expert-major row of the projection buffers [M, B, T+1, d] (CLS has none)
     const int64_t prow = s == 0 ? 0 : (((int64_t)((s - 1) / (T + 1)) * B + b) * (T + 1) + (s - 1) % (T + 1));
     const int pos = pos_ids[r], type = type_ids[r];
@@ -158,10 +170,28 @@ __global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) embed_ln_bwd_ker
     for (int i = 0; i < VEC; ++i)
       F4_OP(de[i], rstd * (gy[i].x - m1 - xh[i].x * m2), rstd * (gy[i].y - m1 - xh[i].y * m2),
             rstd * (gy[i].z - m1 - xh[i].z * m2), rstd * (gy[i].w - m1 - xh[i].w * m2));
+    if (pos != cur_pos) {                                // warp-uniform
+      if (cur_pos >= 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) atomic_add4(dpos_emb + (int64_t)cur_pos * d + 4 * (lane + 32 * i), accp[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) accp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cur_pos = pos;
+    }
+    if (type != cur_type) {
+      if (cur_type >= 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) atomic_add4(dtype_emb + (int64_t)cur_type * d + 4 * (lane + 32 * i), acct[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cur_type = type;
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      atomic_add4(dpos_emb + (int64_t)pos * d + 4 * (lane + 32 * i), de[i]);
-      atomic_add4(dtype_emb + (int64_t)type * d + 4 * (lane + 32 * i), de[i]);
+      accp[i].x += de[i].x; accp[i].y += de[i].y; accp[i].z += de[i].z; accp[i].w += de[i].w;
+      acct[i].x += de[i].x; acct[i].y += de[i].y; acct[i].z += de[i].z; acct[i].w += de[i].w;
     }
     if (s == 0) continue;                                // [CLS] carries no projected feature
     if (invn < 1e12f) {                           // normalize backward: (I - f f^T) de / ||y||
@@ -176,6 +206,14 @@ __global__ void __launch_bounds__(WARPS * 32, VEC <= 4 ? 2 : 1) embed_ln_bwd_ker
     }
     store_row<VEC>(dproj + prow * d, lane, de);
     if (dproj16 != nullptr) store_row16<VEC>(reinterpret_cast<uint16_t*>(dproj16) + prow * d, lane, de, scale16, bf16 != 0);
+  }
+  if (cur_pos >= 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomic_add4(dpos_emb + (int64_t)cur_pos * d + 4 * (lane + 32 * i), accp[i]);
+  }
+  if (cur_type >= 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomic_add4(dtype_emb + (int64_t)cur_type * d + 4 * (lane + 32 * i), acct[i]);
   }
   flush_cols<VEC>(ag, dgamma, lane, warp, red);
   flush_cols<VEC>(ab, dbeta, lane, warp, red);
