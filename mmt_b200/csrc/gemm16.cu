@@ -597,6 +597,20 @@ int make_map16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int6
 
 using namespace mmt;
 
+namespace mmt {
+namespace {
+// CTA pairs of the persistent grid: one per two SMs.  MMT_GEMM16_PAIRS caps it (experiment: leaving SMs to the gradient
+// all-reduce that runs underneath the backward GEMMs did NOT help at N = 2 -- 3.55 ms uncapped, 3.61 / 3.57 / 3.66 ms
+// with 70 / 66 / 60 pairs -- so nothing sets it).
+int gemm16_pairs_limit() {
+  static const int env_cap = [] { const char* e = getenv("MMT_GEMM16_PAIRS"); return e ? atoi(e) : 0; }();
+  int lim = num_sms() / 2;
+  if (env_cap > 0 && env_cap < lim) lim = env_cap;
+  return lim < 1 ? 1 : lim;
+}
+}  // namespace
+}  // namespace mmt
+
 extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   MMT_ARG_CHECK(dp != nullptr, MMT_E_ARG, "mmt_gemm16: null descriptor");
   const mmt_gemm16_desc& d = *dp;
@@ -615,8 +629,9 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   args.num_m_tiles = (d.M + 2 * BM - 1) / (2 * BM);
   // tile width: 256 unless the narrower tiling fills the CTA-pair waves markedly better (see the kernel comment)
   int BN = 256;
+  const int max_pairs = gemm16_pairs_limit();
   {
-    const int pairs_max = num_sms() / 2;
+    const int pairs_max = max_pairs;
     const auto eff = [&](int bn) {
       const long t = (long)args.num_m_tiles * ((d.N + bn - 1) / bn) * d.batch;
       const long rounds = (t + pairs_max - 1) / pairs_max;
@@ -634,7 +649,6 @@ extern "C" int mmt_gemm16(const mmt_gemm16_desc* dp, void* stream_) {
   args.kb_per_split = args.num_kb;
   args.group_m = 2 < args.num_m_tiles ? 2 : args.num_m_tiles;
   const int tiles = args.num_m_tiles * args.num_n_tiles;
-  const int max_pairs = num_sms() / 2;
   if (d.flags & MMT_GEMM_SPLIT_K) {
     MMT_ARG_CHECK(d.batch == 1 && d.C32 && !d.C16 && d.epilogue == MMT_EPI_NONE && !d.add && !d.bias && !d.colsum &&
                   d.p_drop == 0.f, MMT_E_UNSUPPORTED, "mmt_gemm16: split-K needs a plain un-batched fp32 output");
